@@ -1,0 +1,346 @@
+#!/usr/bin/env python
+"""bench.py -- headline measurement of the PROPACK Lanczos-bidiagonalisation hot path on B200.
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload c2|c2-small|c5-1gpu]
+
+One "step" = one complete DLANSVD solve (time to k triplets) of the workload below; the metric is
+whole-job Lanczos steps per second (BASELINE.json metric "time to k triplets + Lanczos steps/s"),
+with the time to k triplets reported as ms_per_step.
+
+Workload at N=1 (BASELINE.json configs[1], "C2"): synthetic random CSR 1M x 1M, ~10 nnz/row, N(0,1)
+values (scipy.sparse.random_array, default_rng(0)), k=50, kmax=600, tol=1e-10, DLANSVD double, CGS
+reorthogonalisation, start vector default_rng(1).uniform.  Inputs (120 MB matrix + 2 x 4.8 GB bases) are
+far larger than the 126 MB L2, so no explicit L2 flush is needed between steps.
+
+Keys (see the task contract): value / ms_per_step are device-timed (CUDA events on the library stream)
+with the matrix and start vector already resident in HBM; e2e goes through the Fortran-ABI `dlansvd_`
+with HOST buffers (matrix upload + start vector up, U/V/sigma back) inside the timed region; roofline is
+the reorthogonalisation GEMV pair, measured live with CUDA events in a profiled solve of the same workload;
+cpu_baseline is the CPU oracle (a port of the reference, OpenMP) on a bounded sample.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (m, n, density, k, kmax, tol)
+    "c2": (1_000_000, 1_000_000, 1e-5, 50, 600, 1e-10),
+    "c2-small": (100_000, 100_000, 1e-4, 50, 600, 1e-10),
+    "c2-tiny": (20_000, 20_000, 5e-4, 10, 200, 1e-10),
+}
+CPU_SAMPLE_STEPS = 150  # Lanczos steps of the same problem the CPU baseline runs per sample
+
+
+def make_matrix(name):
+    import scipy.sparse as sp
+    m, n, dens, k, kmax, tol = WORKLOADS[name]
+    rng = np.random.default_rng(0)
+    A = sp.random_array((m, n), density=dens, format="csr", rng=rng, data_sampler=rng.standard_normal)
+    A.sort_indices()
+    u0 = np.random.default_rng(1).uniform(size=m)
+    return A, u0, k, kmax, tol
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, gpu_index=0):
+        self.proc = None
+        self.lines = []
+        self.gpu = gpu_index
+
+    def start(self):
+        q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "200",
+                                          "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def reorth_bytes(ctr, w=8):
+    """one Gram-Schmidt pass of a length-L vector against l columns moves w*L*(2l+3) bytes."""
+    return w * (2 * ctr["reorth_elems"] + 3 * ctr["reorth_vec_elems"])
+
+
+# ------------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the oracle (a port of the reference; the Fortran cannot be built here)
+# ------------------------------------------------------------------------------------------------------
+def cpu_sample(A, u0, steps):
+    """Time `steps` Lanczos steps (DLANBPRO, k0=0) of the same problem on the host cores. Returns (steps/s, seconds)."""
+    from oracle import oracle_py as O
+    L = O.lib()
+    op = O.Operator(A, np.float64)
+    m, n = A.shape
+    U = np.zeros((m, steps + 1), order="F"); V = np.zeros((n, steps), order="F")
+    U[:, 0] = u0
+    B = np.zeros((steps, 2), order="F")
+    eps = np.finfo(np.float64).eps
+    doption = np.array([np.sqrt(eps), eps ** 0.75, 0.0])
+    ioption = np.array([1, 1], dtype=np.int32)
+    kk, rn, ierr = C.c_int(steps), C.c_double(float(np.linalg.norm(u0))), C.c_int(0)
+    O.stats_reset()
+    t0 = time.perf_counter()
+    L.oracle_lanbpro_d(C.c_int(m), C.c_int(n), C.c_int(0), C.byref(kk), *op.args(), U.ctypes.data_as(C.c_void_p), C.c_long(m),
+                       V.ctypes.data_as(C.c_void_p), C.c_long(n), B.ctypes.data_as(C.c_void_p), C.c_int(steps), C.byref(rn),
+                       doption.ctypes.data_as(C.c_void_p), ioption.ctypes.data_as(C.c_void_p), C.byref(ierr))
+    dt = time.perf_counter() - t0
+    return O.stats()["nsteps"] / dt, dt, int(L.oracle_num_threads())
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    A, u0, k, kmax, tol = make_matrix(args.workload)
+    vals, secs, cores = [], [], 1
+    for i in range(args.warmup + args.steps):
+        v, dt, cores = cpu_sample(A, u0, CPU_SAMPLE_STEPS)
+        if i >= args.warmup:
+            vals.append(v); secs.append(dt)
+    value = float(np.mean(vals))
+    sample = (f"oracle DLANBPRO (C++/OpenMP port of the reference; Fortran not buildable here), first {CPU_SAMPLE_STEPS} "
+              f"Lanczos steps of the {args.workload} problem incl. partial reorthogonalisation, OpenMP CSR/CSC APROD")
+    line = {
+        "impl": "reference", "metric": "lanczos_steps_per_s", "value": value, "unit": "steps/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * float(np.mean(secs)), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": config_dict(args.workload, A, k, kmax, tol),
+        "cpu_baseline": {"value": value, "unit": "steps/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def config_dict(name, A, k, kmax, tol):
+    return {"workload": f"BASELINE configs[1] '{name}': synthetic random CSR {A.shape[0]}x{A.shape[1]}, nnz={A.nnz} "
+                        f"(~{A.nnz / A.shape[0]:.1f}/row), k={k}, kmax={kmax}, tol={tol:g}, DLANSVD double, CGS, ELR",
+            "driver": "dlansvd", "k": k, "kmax": kmax, "tol": tol, "nnz": int(A.nnz), "rows": int(A.shape[0]),
+            "cols": int(A.shape[1]), "l2_policy": "inputs larger than L2 (no flush needed)"}
+
+
+# ------------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    import propack_b200
+    from propack_b200 import _lib, f77
+    L = _lib.lib()
+    _lib.check(L.propack_b200_init(), "init")
+    stream = torch.cuda.current_stream()
+    _lib.check(L.propack_b200_set_stream(C.c_void_p(stream.cuda_stream)), "set_stream")
+
+    A, u0, k, kmax, tol = make_matrix(args.workload)
+    m, n = A.shape
+    op = f77.Operator(A)                       # matrix resident in HBM from here on
+    lanmax = min(m + 1, n + 1, kmax)
+    solver = _lib.check(L.propack_b200_solver_create(C.c_int(op.handle), C.c_int(lanmax + 1), C.c_int(lanmax)), "solver_create")
+    eps = np.finfo(np.float64).eps
+
+    def solve_resident():
+        _lib.check(L.propack_b200_solver_set_start(C.c_int(solver), u0.ctypes.data_as(C.c_void_p)), "set_start")
+        sigma = np.zeros(k); bnd = np.zeros(k)
+        dopt = np.array([np.sqrt(eps), eps ** 0.75, 0.0]); iopt = np.array([1, 1], dtype=np.int32)
+        kk, info = C.c_int(k), C.c_int(0)
+        propack_b200.reset_counters()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record(stream)
+        _lib.check(L.propack_b200_solver_lansvd(C.c_int(solver), C.c_int(1), C.c_int(1), C.byref(kk), C.c_int(kmax),
+                                                sigma.ctypes.data_as(C.c_void_p), bnd.ctypes.data_as(C.c_void_p), C.c_double(tol),
+                                                dopt.ctypes.data_as(C.c_void_p), iopt.ctypes.data_as(C.c_void_p), C.byref(info)), "lansvd")
+        e1.record(stream)
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1), propack_b200.counters(), sigma[:kk.value], kk.value, info.value
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        solve_resident()
+    clocks = ClockSampler(local)
+    barrier()
+    clocks.start()
+    times, steps_total, launches, last = [], 0, 0, None
+    for _ in range(args.steps):
+        ms, ctr, sigma, kc, info = solve_resident()
+        times.append(ms); steps_total += ctr["nsteps"]; launches += ctr["launches"]; last = (ctr, sigma, kc, info)
+    barrier()
+    clk = clocks.stop()
+    total_ms = float(np.sum(times))
+    if world > 1:
+        t = torch.tensor([total_ms], device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX); total_ms = float(t.item())
+        s = torch.tensor([float(steps_total)], device="cuda"); dist.all_reduce(s); steps_total = int(s.item())
+    value = steps_total / (total_ms * 1e-3)
+
+    # ---- roofline: reorthogonalisation GEMV pair, CUDA-event phase timers in one profiled solve ------------
+    propack_b200.set_profile(True)
+    _, pctr, _, _, _ = solve_resident()
+    ph = propack_b200.phase_ms()
+    propack_b200.set_profile(False)
+    peak, peak_src = peaks()
+    rb = reorth_bytes(pctr)
+    reorth_ms = ph["reorth"]["ms"]
+    achieved = rb / (reorth_ms * 1e-3) / 1e9 if reorth_ms > 0 else 0.0
+    spmv_bytes = (pctr["nopx"] / 2.0) * (op.bytes_per_product(False) + op.bytes_per_product(True) + 8.0 * (m + n))
+    spmv_gbs = spmv_bytes / (ph["aprod"]["ms"] * 1e-3) / 1e9 if ph["aprod"]["ms"] > 0 else 0.0
+    # isolated kernels (device-resident synthetic operands, L2 flushed between launches)
+    L.propack_b200_bench_reorth_d.argtypes = [C.c_long, C.c_int, C.c_int, C.c_int]
+    iso = {}
+    for l in (64, 256):
+        t_ms = L.propack_b200_bench_reorth_d(m, l, 5, 1)
+        iso[f"reorth_L{m}_l{l}_gbs"] = 8.0 * m * (2 * l + 3) / (t_ms * 1e-3) / 1e9
+    for adj in (0, 1):
+        t_ms = L.propack_b200_bench_spmv(C.c_int(op.handle), C.c_int(adj), C.c_int(10), C.c_int(1))
+        iso[f"spmv_{'t' if adj else 'n'}_gbs"] = (op.bytes_per_product(bool(adj)) + 8.0 * (n if adj else m)) / (t_ms * 1e-3) / 1e9
+
+    # ---- e2e: Fortran-ABI dlansvd_ with host buffers (matrix upload, start vector up, U/V/sigma down) --------
+    rp = np.ascontiguousarray(A.indptr, dtype=np.int32); ci = np.ascontiguousarray(A.indices, dtype=np.int32)
+    va = np.ascontiguousarray(A.data)
+    pin = lambda a: torch.from_numpy(a).pin_memory().numpy()
+    rp, ci, va, u0p = pin(rp), pin(ci), pin(va), pin(u0)
+
+    def solve_e2e():
+        t0 = time.perf_counter()
+        op2 = f77.Operator.__new__(f77.Operator)
+        h = _lib.check(L.propack_b200_csr_create_d(C.c_int(m), C.c_int(n), rp.ctypes.data_as(C.c_void_p), ci.ctypes.data_as(C.c_void_p),
+                                                    va.ctypes.data_as(C.c_void_p), C.c_int(0)), "csr_create")
+        op2.handle, op2._cb, op2.dtype, op2.pfx, op2.shape = h, None, np.dtype(np.float64), "d", (m, n)
+        op2.iparm = np.array([h, 0], dtype=np.int32); op2.parm = np.zeros(2)
+        r = f77.lansvd(op2, k, kmax, tol=tol, u0=u0p, cgs=True)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        op2.close()
+        return dt, r
+
+    _lib.check(L.propack_b200_solver_destroy(C.c_int(solver)), "solver_destroy")  # free the resident bases first
+    e2e_t, e2e_steps = [], 0
+    for i in range(1 + max(1, min(args.steps, 3))):
+        propack_b200.reset_counters()
+        dt, r = solve_e2e()
+        if i >= 1:
+            e2e_t.append(dt); e2e_steps += propack_b200.counters()["nsteps"]
+    e2e_val = e2e_steps / float(np.sum(e2e_t))
+    if world > 1:
+        t = torch.tensor([float(np.sum(e2e_t))], device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        s = torch.tensor([float(e2e_steps)], device="cuda"); dist.all_reduce(s)
+        e2e_val = float(s.item()) / float(t.item())
+    h2d = rp.nbytes + ci.nbytes + va.nbytes + u0.nbytes
+    d2h = (m + n) * k * 8 + 2 * k * 8
+
+    # ---- cpu baseline (rank 0, N=1 only): bounded sample of the same workload on the host cores --------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        v, dt, cores = cpu_sample(A, u0, CPU_SAMPLE_STEPS)
+        cpu = {"value": v, "unit": "steps/s", "cores": cores, "kind": "port",
+               "sample": f"oracle DLANBPRO (C++/OpenMP port; the Fortran reference cannot be compiled in this image), first "
+                         f"{CPU_SAMPLE_STEPS} Lanczos steps of the same problem ({dt:.1f} s); early steps reorthogonalise against "
+                         f"fewer columns than the run average, so this overstates the CPU rate"}
+    if rank == 0:
+        ctr, sigma, kc, info = last
+        line = {
+            "metric": "lanczos_steps_per_s", "value": value, "unit": "steps/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": dict(config_dict(args.workload, A, k, kmax, tol),
+                           parallelism=("single GPU" if world == 1 else f"{world} independent replicas (row-sharded path not in this round)")),
+            "time_to_k_triplets_s": total_ms / args.steps / 1e3, "lanczos_steps_per_solve": ctr["nsteps"],
+            "converged": kc, "info": info, "sigma_1": float(sigma[0]) if kc else None, "sigma_k": float(sigma[-1]) if kc else None,
+            "gpu_launches": int(launches), "host_syncs_per_solve": ctr["host_syncs"],
+            "e2e": {"value": e2e_val, "unit": "steps/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "time_to_k_triplets_s": float(np.mean(e2e_t)),
+                    "path": "propack_b200_csr_create_d + dlansvd_ (Fortran ABI, pinned host CSR / start vector; U,V,sigma copied back)"},
+            "roofline": {"bound": "hbm", "kernel": "reorthogonalisation GEMV pair (gemv_t_kernel + gemv_t_finalize + gemv_n_kernel)",
+                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
+                         "frac_of_nominal_8000": achieved / 8000.0, "traffic": None,
+                         "algorithmic_bytes": rb, "kernel_ms_in_solve": reorth_ms, "share_of_solve": reorth_ms / sum(v["ms"] for v in ph.values()),
+                         "how": "CUDA-event phase timers on the library stream in one extra profiled solve of the same workload"},
+            "spmv": {"achieved_gbs_in_solve": spmv_gbs, "frac": spmv_gbs / peak, "aprod_ms_in_solve": ph["aprod"]["ms"]},
+            "isolated_kernels_gbs": iso,
+            "phases_ms": {kname: v["ms"] for kname, v in ph.items()},
+            "clocks": clk,
+        }
+        if cpu:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

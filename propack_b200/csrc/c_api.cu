@@ -1,0 +1,816 @@
+// propack_b200 -- the C-ABI (include/propack_b200.h): Fortran-ABI drivers of the reference library,
+// device-resident operator handles, solver sessions, counters.  Host buffers are staged here; the
+// numerical work is in engine.hpp / the .cu kernels.  Nothing in this file computes on the CPU
+// except the O(k^2) bidiagonal algebra the reference also keeps on the host.
+#include <cstdarg>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <numeric>
+#include <string>
+
+#include "../../include/propack_b200.h"
+#include "engine.hpp"
+
+using namespace pb;
+
+extern "C" {
+struct pb200_timing_common timing_;
+}
+
+namespace {
+
+std::string g_last_error;
+void set_error(const std::string& s) { g_last_error = s; }
+
+int error_code(const std::exception& e) {
+  set_error(e.what());
+  if (auto* ce = dynamic_cast<const CudaError*>(&e)) return -100 - (int)ce->code;
+  return -99;
+}
+#define PB_API_TRY try {
+#define PB_API_CATCH(ret_stmt)             \
+  }                                        \
+  catch (const std::exception& e) {        \
+    int code__ = error_code(e);            \
+    (void)code__;                          \
+    ret_stmt;                              \
+  }
+
+template <class T> struct abi;  // maps the ABI struct types onto the kernel scalar types
+template <> struct abi<float> { using type = float; static constexpr char tag = 's'; };
+template <> struct abi<double> { using type = double; static constexpr char tag = 'd'; };
+template <> struct abi<cplx<float>> { using type = pb200_complex8; static constexpr char tag = 'c'; };
+template <> struct abi<cplx<double>> { using type = pb200_complex16; static constexpr char tag = 'z'; };
+
+struct OpEntry {
+  char tag = 0;
+  int kind = 0;  // 0 csr, 1 dense
+  std::shared_ptr<void> op;
+};
+struct SolverEntry {
+  char tag = 0;
+  int op_handle = 0;
+  std::shared_ptr<void> engine;
+};
+std::map<int, OpEntry> g_ops;
+std::map<int, SolverEntry> g_solvers;
+int g_next_op = 1, g_next_solver = 1;
+
+template <class T> LinOp<T>* lookup_op(int handle) {
+  auto it = g_ops.find(handle);
+  if (it == g_ops.end()) throw std::runtime_error("propack_b200: unknown operator handle " + std::to_string(handle));
+  if (it->second.tag != abi<T>::tag) throw std::runtime_error("propack_b200: operator handle has a different precision");
+  return static_cast<LinOp<T>*>(it->second.op.get());
+}
+
+bool is_yes(const char* c) { return c && (*c == 'y' || *c == 'Y'); }
+
+// ---------------------------------------------------------------------------------------------------
+// CSR registration: upload, device-independent host analysis of row lengths, transpose.
+// ---------------------------------------------------------------------------------------------------
+struct RowBins { int lpr; std::vector<int> med, lng; };
+RowBins analyze_rows(const int* rp, int rows) {
+  RowBins b;
+  const double mean = rows > 0 ? double(rp[rows] - rp[0]) / rows : 0.0;
+  b.lpr = mean <= 3 ? 2 : mean <= 6 ? 4 : mean <= 12 ? 8 : mean <= 24 ? 16 : 32;
+  if (const char* e = std::getenv("PROPACK_B200_SPMV_LPR")) {
+    int v = std::atoi(e);
+    if (v == 2 || v == 4 || v == 8 || v == 16 || v == 32) b.lpr = v;
+  }
+  const int short_max = 4 * b.lpr;
+  for (int i = 0; i < rows; ++i) {
+    const int len = rp[i + 1] - rp[i];
+    if (len > kCsrLongRow) b.lng.push_back(i);
+    else if (len > short_max) b.med.push_back(i);
+  }
+  return b;
+}
+
+// Stable counting-sort transpose on the host: CSR(A) -> CSR(A^T) with sorted row indices inside each
+// column -- the unique canonical form, identical to scipy's tocsc() / (A.T).tocsr() with sorted indices.
+template <class T>
+void transpose_csr(int m, int n, const int* rp, const int* ci, const T* va, std::vector<int>& trp, std::vector<int>& tci,
+                   std::vector<T>& tva) {
+  const long nnz = rp[m];
+  trp.assign((size_t)n + 1, 0);
+  tci.resize(nnz); tva.resize(nnz);
+  for (long p = 0; p < nnz; ++p) trp[ci[p] + 1] += 1;
+  for (int j = 0; j < n; ++j) trp[j + 1] += trp[j];
+  std::vector<int> next(trp.begin(), trp.end() - 1);
+  for (int i = 0; i < m; ++i)
+    for (int p = rp[i]; p < rp[i + 1]; ++p) {
+      const int q = next[ci[p]]++;
+      tci[q] = i; tva[q] = va[p];
+    }
+}
+
+template <class T> void fill_device_csr(CsrDevice<T>& D, int rows, int cols, long nnz, const DeviceBuffer<int>& rp,
+                                        const DeviceBuffer<int>& ci, const DeviceBuffer<T>& va, const RowBins& b,
+                                        DeviceBuffer<int>& bins) {
+  D.rows = rows; D.cols = cols; D.nnz = nnz; D.rp = rp.p; D.ci = ci.p; D.va = va.p;
+  D.lanes_per_row = b.lpr;
+  D.n_med = (int)b.med.size(); D.n_long = (int)b.lng.size();
+  bins.alloc(b.med.size() + b.lng.size() + 1);
+  if (!b.med.empty()) PB_CUDA(cudaMemcpy(bins.p, b.med.data(), sizeof(int) * b.med.size(), cudaMemcpyHostToDevice));
+  if (!b.lng.empty()) PB_CUDA(cudaMemcpy(bins.p + b.med.size(), b.lng.data(), sizeof(int) * b.lng.size(), cudaMemcpyHostToDevice));
+  D.med_rows = bins.p; D.long_rows = bins.p + b.med.size();
+}
+
+template <class T> int csr_create(int m, int n, const int* rowptr, const int* colind, const void* values_, int base) {
+  PB_API_TRY
+  Context::get();
+  const T* values = static_cast<const T*>(values_);
+  if (m <= 0 || n <= 0 || !rowptr || !colind || !values) throw std::runtime_error("propack_b200: bad CSR arguments");
+  const long nnz = (long)rowptr[m] - base;
+  std::vector<int> rp(m + 1), ci(nnz);
+  for (int i = 0; i <= m; ++i) rp[i] = rowptr[i] - base;
+  for (long p = 0; p < nnz; ++p) {
+    ci[p] = colind[p] - base;
+    if (ci[p] < 0 || ci[p] >= n) throw std::runtime_error("propack_b200: CSR column index out of range");
+  }
+  // canonical form: sort indices inside each row if needed (stable w.r.t. values)
+  for (int i = 0; i < m; ++i) {
+    bool sorted = true;
+    for (int p = rp[i] + 1; p < rp[i + 1]; ++p) if (ci[p - 1] > ci[p]) { sorted = false; break; }
+    if (!sorted) throw std::runtime_error("propack_b200: CSR column indices must be sorted within each row");
+  }
+  auto op = std::make_shared<CsrOperator<T>>();
+  op->m = m; op->n = n;
+  std::vector<int> trp, tci; std::vector<T> tva;
+  transpose_csr<T>(m, n, rp.data(), ci.data(), values, trp, tci, tva);
+  op->rp.alloc(m + 1); op->ci.alloc(std::max<long>(nnz, 1)); op->va.alloc(std::max<long>(nnz, 1));
+  op->trp.alloc(n + 1); op->tci.alloc(std::max<long>(nnz, 1)); op->tva.alloc(std::max<long>(nnz, 1));
+  PB_CUDA(cudaMemcpy(op->rp.p, rp.data(), sizeof(int) * (m + 1), cudaMemcpyHostToDevice));
+  PB_CUDA(cudaMemcpy(op->trp.p, trp.data(), sizeof(int) * (n + 1), cudaMemcpyHostToDevice));
+  if (nnz) {
+    PB_CUDA(cudaMemcpy(op->ci.p, ci.data(), sizeof(int) * nnz, cudaMemcpyHostToDevice));
+    PB_CUDA(cudaMemcpy(op->va.p, values, sizeof(T) * nnz, cudaMemcpyHostToDevice));
+    PB_CUDA(cudaMemcpy(op->tci.p, tci.data(), sizeof(int) * nnz, cudaMemcpyHostToDevice));
+    PB_CUDA(cudaMemcpy(op->tva.p, tva.data(), sizeof(T) * nnz, cudaMemcpyHostToDevice));
+  }
+  fill_device_csr<T>(op->A, m, n, nnz, op->rp, op->ci, op->va, analyze_rows(rp.data(), m), op->bins);
+  fill_device_csr<T>(op->At, n, m, nnz, op->trp, op->tci, op->tva, analyze_rows(trp.data(), n), op->tbins);
+  OpEntry e; e.tag = abi<T>::tag; e.kind = 0; e.op = op;
+  const int h = g_next_op++;
+  g_ops[h] = e;
+  return h;
+  PB_API_CATCH(return code__)
+}
+
+template <class T> int dense_create(int m, int n, const void* A_, long lda, bool adopt_device) {
+  PB_API_TRY
+  Context& c = Context::get();
+  auto op = std::make_shared<DenseOperator<T>>();
+  op->m = m; op->n = n;
+  if (adopt_device) {
+    op->A = static_cast<const T*>(A_); op->lda = lda;
+  } else {
+    const long ld = Engine<T>::pad_ld(m);
+    op->store.alloc((size_t)ld * n);
+    PB_CUDA(cudaMemsetAsync(op->store.p, 0, sizeof(T) * (size_t)ld * n, c.stream));
+    PB_CUDA(cudaMemcpy2DAsync(op->store.p, sizeof(T) * ld, A_, sizeof(T) * lda, sizeof(T) * m, n, cudaMemcpyHostToDevice, c.stream));
+    c.sync();
+    op->A = op->store.p; op->lda = ld;
+  }
+  OpEntry e; e.tag = abi<T>::tag; e.kind = 1; e.op = op;
+  const int h = g_next_op++;
+  g_ops[h] = e;
+  return h;
+  PB_API_CATCH(return code__)
+}
+
+// ---------------------------------------------------------------------------------------------------
+// operator resolution for the Fortran-ABI entry points
+// ---------------------------------------------------------------------------------------------------
+template <class T> void* builtin_aprod();
+template <> void* builtin_aprod<float>() { return (void*)&propack_b200_aprod_s_; }
+template <> void* builtin_aprod<double>() { return (void*)&propack_b200_aprod_d_; }
+template <> void* builtin_aprod<cplx<float>>() { return (void*)&propack_b200_aprod_c_; }
+template <> void* builtin_aprod<cplx<double>>() { return (void*)&propack_b200_aprod_z_; }
+
+template <class T> struct ResolvedOp {
+  LinOp<T>* op = nullptr;
+  CallbackOperator<T> cb;
+  ResolvedOp(void* aprod, int m, int n, void* parm, int* iparm) {
+    if (aprod == builtin_aprod<T>()) {
+      if (!iparm) throw std::runtime_error("propack_b200: built-in APROD needs the operator handle in iparm(1)");
+      op = lookup_op<T>(iparm[0]);
+      if (op->m != m || op->n != n) throw std::runtime_error("propack_b200: m,n do not match the registered operator");
+    } else {
+      if (!aprod) throw std::runtime_error("propack_b200: APROD is null");
+      cb.m = m; cb.n = n; cb.fn = (aprod_f77_t<T>)aprod; cb.parm = parm; cb.iparm = iparm;
+      op = &cb;
+    }
+  }
+};
+
+void publish_timing(const Context& c) {  // keep the reference's COMMON /timing/ counters live (stat.h:7-15)
+  timing_.nopx = (int)c.ctr.nopx; timing_.nreorth = (int)c.ctr.nreorth; timing_.ndot = (int)c.ctr.ndot;
+  timing_.nitref = (int)c.ctr.nitref; timing_.nrestart = (int)c.ctr.nrestart; timing_.nbsvd = (int)c.ctr.nbsvd;
+  timing_.nlandim = (int)c.ctr.nlandim; timing_.nsing = (int)c.ctr.nsing;
+  timing_.tmvopx = (float)(c.ctr.phase_ms[PH_APROD] * 1e-3); timing_.treorth = (float)(c.ctr.phase_ms[PH_REORTH] * 1e-3);
+  timing_.tgetu0 = (float)(c.ctr.phase_ms[PH_GETU0] * 1e-3); timing_.tritzvec = (float)(c.ctr.phase_ms[PH_RITZ] * 1e-3);
+  timing_.trestart = (float)(c.ctr.phase_ms[PH_RESTART] * 1e-3); timing_.tbsvd = (float)(c.ctr.phase_ms[PH_HOST_BSVD] * 1e-3);
+}
+
+template <class T> void upload_cols(Context& c, T* dst, long ldd, const void* src, long lds, long rows, int cols) {
+  if (cols <= 0 || rows <= 0) return;
+  PB_CUDA(cudaMemcpy2DAsync(dst, sizeof(T) * ldd, src, sizeof(T) * lds, sizeof(T) * rows, cols, cudaMemcpyHostToDevice, c.stream));
+}
+template <class T> void download_cols(Context& c, void* dst, long ldd, const T* src, long lds, long rows, int cols) {
+  if (cols <= 0 || rows <= 0) return;
+  PB_CUDA(cudaMemcpy2DAsync(dst, sizeof(T) * ldd, src, sizeof(T) * lds, sizeof(T) * rows, cols, cudaMemcpyDeviceToHost, c.stream));
+}
+
+// ---------------------------------------------------------------------------------------------------
+// drivers
+// ---------------------------------------------------------------------------------------------------
+template <class T>
+void lansvd_entry(const char* jobu, const char* jobv, int m, int n, int* k, int kmax, void* aprod, void* U, int ldu,
+                  real_t<T>* sigma, real_t<T>* bnd, void* V, int ldv, real_t<T> tolin, real_t<T>* option, int* ioption, int* info,
+                  void* parm, int* iparm) {
+  PB_API_TRY
+  Context& c = Context::get();
+  ResolvedOp<T> ro(aprod, m, n, parm, iparm);
+  const int lanmax = std::min(std::min(n + 1, m + 1), kmax);
+  Engine<T> eng(c, ro.op, lanmax + 1, std::max(lanmax, 1));
+  upload_cols<T>(c, eng.U, eng.ldu, U, ldu, m, 1);
+  const bool ju = is_yes(jobu), jv = is_yes(jobv);
+  *info = eng.lansvd(ju, jv, *k, kmax, sigma, bnd, tolin, option, ioption);
+  if (ju) download_cols<T>(c, U, ldu, eng.U, eng.ldu, m, *k);
+  if (jv) download_cols<T>(c, V, ldv, eng.V, eng.ldv, n, *k);
+  c.sync();
+  publish_timing(c);
+  PB_API_CATCH(*info = code__)
+}
+
+template <class T>
+void lansvd_irl_entry(const char* which, const char* jobu, const char* jobv, int m, int n, int* dim, int p, int* neig, int maxiter,
+                      void* aprod, void* U, int ldu, real_t<T>* sigma, real_t<T>* bnd, void* V, int ldv, real_t<T> tolin,
+                      real_t<T>* option, int* ioption, int* info, void* parm, int* iparm) {
+  PB_API_TRY
+  Context& c = Context::get();
+  ResolvedOp<T> ro(aprod, m, n, parm, iparm);
+  const int d = std::min(*dim, std::min(n + 1, m + 1));
+  Engine<T> eng(c, ro.op, d + 1, std::max(d, 1));
+  upload_cols<T>(c, eng.U, eng.ldu, U, ldu, m, 1);
+  const bool ju = is_yes(jobu), jv = is_yes(jobv);
+  const bool smallest = which && (*which == 's' || *which == 'S');
+  *info = eng.lansvd_irl(smallest, ju, jv, *dim, p, *neig, maxiter, sigma, bnd, tolin, option, ioption);
+  if (ju) download_cols<T>(c, U, ldu, eng.U, eng.ldu, m, *neig);
+  if (jv) download_cols<T>(c, V, ldv, eng.V, eng.ldv, n, *neig);
+  c.sync();
+  publish_timing(c);
+  PB_API_CATCH(*info = code__)
+}
+
+template <class T>
+void lanbpro_entry(int m, int n, int k0, int* k, void* aprod, void* U, int ldu, void* V, int ldv, real_t<T>* B, int ldb,
+                   real_t<T>* rnorm, real_t<T>* option, int* ioption, void* parm, int* iparm, int* ierr) {
+  PB_API_TRY
+  Context& c = Context::get();
+  ResolvedOp<T> ro(aprod, m, n, parm, iparm);
+  const int kin = *k;
+  Engine<T> eng(c, ro.op, kin + 1, std::max(kin, 1));
+  upload_cols<T>(c, eng.U, eng.ldu, U, ldu, m, k0 + 1);
+  upload_cols<T>(c, eng.V, eng.ldv, V, ldv, n, k0);
+  *ierr = eng.lanbpro(k0, *k, B, B + ldb, *rnorm, option, ioption);
+  download_cols<T>(c, U, ldu, eng.U, eng.ldu, m, kin + 1);
+  download_cols<T>(c, V, ldv, eng.V, eng.ldv, n, kin);
+  c.sync();
+  publish_timing(c);
+  PB_API_CATCH(*ierr = code__)
+}
+
+template <class T> struct NullOp : LinOp<T> {
+  void apply(Context&, bool, const T*, T*, real_t<T>, const T*, Pending*) override {
+    throw std::runtime_error("propack_b200: internal: NullOp applied");
+  }
+  double algorithmic_bytes(bool) const override { return 0; }
+};
+
+template <class T>
+void reorth_entry(int n, int k, const void* V, int ldv, void* vnew, real_t<T>* normvnew, const int* index, real_t<T> alpha, int iflag) {
+  PB_API_TRY
+  if (k <= 0 || n <= 0) return;
+  Context& c = Context::get();
+  NullOp<T> nop; nop.m = n; nop.n = 1;
+  Engine<T> eng(c, &nop, k + 1, 1);
+  upload_cols<T>(c, eng.U, eng.ldu, V, ldv, n, k);
+  upload_cols<T>(c, eng.ucol(k + 1), eng.ldu, vnew, n, n, 1);
+  host::IntervalList idx(2 * k + 4);
+  for (int i = 0; i < 2 * k + 3; ++i) {
+    idx.v[i] = index[i];
+    if ((i % 2 == 0) && (index[i] > k || index[i] <= 0)) break;
+  }
+  eng.reorth(n, k, eng.U, eng.ldu, eng.ucol(k + 1), *normvnew, idx, alpha, iflag);
+  download_cols<T>(c, vnew, n, eng.ucol(k + 1), eng.ldu, n, 1);
+  c.sync();
+  publish_timing(c);
+  PB_API_CATCH(*normvnew = real_t<T>(-1))
+}
+
+template <class T>
+void getu0_entry(const char* transa, int m, int n, int j, int ntry, void* u0, real_t<T>* u0norm, const void* Ub, int ldu, void* aprod,
+                 void* parm, int* iparm, int* ierr, int icgs, real_t<T>* anormest) {
+  PB_API_TRY
+  Context& c = Context::get();
+  ResolvedOp<T> ro(aprod, m, n, parm, iparm);
+  const bool adjoint = !(transa && (*transa == 'n' || *transa == 'N'));
+  Engine<T> eng(c, ro.op, adjoint ? 1 : j + 1, adjoint ? j + 1 : 1);
+  T* basis = adjoint ? eng.V : eng.U;
+  const long ld = adjoint ? eng.ldv : eng.ldu;
+  const long rows = adjoint ? n : m;
+  upload_cols<T>(c, basis, ld, Ub, ldu, rows, j);
+  T* out = basis + (size_t)j * ld;
+  eng.getu0(adjoint, j, ntry, out, *u0norm, basis, ld, *ierr, icgs, *anormest);
+  download_cols<T>(c, u0, rows, out, ld, rows, 1);
+  c.sync();
+  publish_timing(c);
+  PB_API_CATCH(*ierr = code__)
+}
+
+template <class T> void safescal_entry(int n, real_t<T> alpha, void* x) {
+  PB_API_TRY
+  if (n <= 0) return;
+  Context& c = Context::get();
+  NullOp<T> nop; nop.m = n; nop.n = 1;
+  Engine<T> eng(c, &nop, 1, 1);
+  upload_cols<T>(c, eng.U, eng.ldu, x, n, n, 1);
+  eng.safescal(n, alpha, eng.U);
+  download_cols<T>(c, x, n, eng.U, eng.ldu, n, 1);
+  c.sync();
+  PB_API_CATCH(return )
+}
+
+// A(m x k) <- alpha * A * op(B): result m x n (dgemm_ovwr.F:56-87)
+template <class T>
+void gemm_ovwr_left_entry(const char* transb, int m, int n, int k, real_t<T> alpha, void* A, int lda, const real_t<T>* B, int ldb) {
+  using R = real_t<T>;
+  PB_API_TRY
+  if (m <= 0 || n <= 0 || k <= 0) return;
+  Context& c = Context::get();
+  const bool tr = transb && (*transb == 't' || *transb == 'T');
+  std::vector<R> W((size_t)k * n);  // W(l,jn) = alpha * op(B)(l,jn)
+  for (int jn = 0; jn < n; ++jn)
+    for (int l = 0; l < k; ++l) W[(size_t)jn * k + l] = alpha * (tr ? B[(size_t)l * ldb + jn] : B[(size_t)jn * ldb + l]);
+  NullOp<T> nop; nop.m = m; nop.n = 1;
+  Engine<T> eng(c, &nop, std::max(k, n), 1);
+  upload_cols<T>(c, eng.U, eng.ldu, A, lda, m, k);
+  k_gemm_tall<T>(c, m, n, k, eng.U, eng.ldu, W.data());
+  download_cols<T>(c, A, lda, eng.U, eng.ldu, m, n);
+  c.sync();
+  PB_API_CATCH(return )
+}
+
+template <class T> void aprod_entry(const char* transa, int m, int n, const void* x, void* y, int* iparm) {
+  PB_API_TRY
+  Context& c = Context::get();
+  LinOp<T>* op = lookup_op<T>(iparm[0]);
+  const bool adjoint = !(transa && (*transa == 'n' || *transa == 'N'));
+  const long nx = adjoint ? m : n, ny = adjoint ? n : m;
+  DeviceBuffer<T> dx(Engine<T>::pad_ld(nx)), dy(Engine<T>::pad_ld(ny));
+  PB_CUDA(cudaMemsetAsync(dx.p, 0, sizeof(T) * dx.n, c.stream));
+  PB_CUDA(cudaMemsetAsync(dy.p, 0, sizeof(T) * dy.n, c.stream));
+  PB_CUDA(cudaMemcpyAsync(dx.p, x, sizeof(T) * nx, cudaMemcpyHostToDevice, c.stream));
+  op->apply(c, adjoint, dx.p, dy.p, real_t<T>(0), nullptr, nullptr);
+  PB_CUDA(cudaMemcpyAsync(y, dy.p, sizeof(T) * ny, cudaMemcpyDeviceToHost, c.stream));
+  c.sync();
+  PB_API_CATCH(fprintf(stderr, "%s\n", g_last_error.c_str()))
+}
+
+// ---------------------------------------------------------------------------------------------------
+// solver sessions
+// ---------------------------------------------------------------------------------------------------
+template <class T> int solver_create_t(int op_handle, int ucols, int vcols) {
+  Context& c = Context::get();
+  LinOp<T>* op = lookup_op<T>(op_handle);
+  auto eng = std::make_shared<Engine<T>>(c, op, ucols, vcols);
+  SolverEntry e; e.tag = abi<T>::tag; e.op_handle = op_handle; e.engine = eng;
+  const int id = g_next_solver++;
+  g_solvers[id] = e;
+  c.sync();
+  return id;
+}
+SolverEntry& find_solver(int id) {
+  auto it = g_solvers.find(id);
+  if (it == g_solvers.end()) throw std::runtime_error("propack_b200: unknown solver id");
+  return it->second;
+}
+template <class F> auto dispatch(char tag, F f) {
+  switch (tag) {
+    case 's': return f((float*)nullptr);
+    case 'd': return f((double*)nullptr);
+    case 'c': return f((cplx<float>*)nullptr);
+    default: return f((cplx<double>*)nullptr);
+  }
+}
+
+}  // namespace
+
+// =====================================================================================================
+// extern "C"
+// =====================================================================================================
+extern "C" {
+
+#define PB_DRIVERS_REAL(P, T, R, APT)                                                                                        \
+  void P##lansvd_(const char* jobu, const char* jobv, const int* m, const int* n, int* k, const int* kmax, APT aprod, R* U,    \
+                  const int* ldu, R* sigma, R* bnd, R* V, const int* ldv, const R* tolin, R* work, const int* lwork, int* iwork, \
+                  const int* liwork, R* option, int* ioption, int* info, R* parm, int* iparm, size_t, size_t) {                  \
+    (void)work; (void)lwork; (void)iwork; (void)liwork;                                                                          \
+    lansvd_entry<T>(jobu, jobv, *m, *n, k, *kmax, (void*)aprod, U, *ldu, sigma, bnd, V, *ldv, *tolin, option, ioption, info,    \
+                    parm, iparm);                                                                                                \
+  }                                                                                                                              \
+  void P##lansvd_irl_(const char* which, const char* jobu, const char* jobv, const int* m, const int* n, int* dim, const int* p, \
+                      int* neig, const int* maxiter, APT aprod, R* U, const int* ldu, R* sigma, R* bnd, R* V, const int* ldv,    \
+                      const R* tolin, R* work, const int* lwork, int* iwork, const int* liwork, R* option, int* ioption,         \
+                      int* info, R* parm, int* iparm, size_t, size_t, size_t) {                                                  \
+    (void)work; (void)lwork; (void)iwork; (void)liwork;                                                                          \
+    lansvd_irl_entry<T>(which, jobu, jobv, *m, *n, dim, *p, neig, *maxiter, (void*)aprod, U, *ldu, sigma, bnd, V, *ldv, *tolin,  \
+                        option, ioption, info, parm, iparm);                                                                     \
+  }                                                                                                                              \
+  void P##lanbpro_(const int* m, const int* n, const int* k0, int* k, APT aprod, R* U, const int* ldu, R* V, const int* ldv,     \
+                   R* B, const int* ldb, R* rnorm, R* option, int* ioption, R* work, int* iwork, R* parm, int* iparm,            \
+                   int* ierr) {                                                                                                  \
+    (void)work; (void)iwork;                                                                                                     \
+    lanbpro_entry<T>(*m, *n, *k0, k, (void*)aprod, U, *ldu, V, *ldv, B, *ldb, rnorm, option, ioption, parm, iparm, ierr);        \
+  }                                                                                                                              \
+  void P##gemm_ovwr_left_(const char* transb, const int* m, const int* n, const int* k, const R* alpha, R* A, const int* lda,    \
+                          const R* beta, const R* B, const int* ldb, R* work, const int* lwork, size_t) {                        \
+    (void)beta; (void)work; (void)lwork;                                                                                         \
+    gemm_ovwr_left_entry<T>(transb, *m, *n, *k, *alpha, A, *lda, B, *ldb);                                                       \
+  }
+
+#define PB_DRIVERS_CPLX(P, T, R, CT, APT, GEMMNAME)                                                                             \
+  void P##lansvd_(const char* jobu, const char* jobv, const int* m, const int* n, int* k, const int* kmax, APT aprod, CT* U,     \
+                  const int* ldu, R* sigma, R* bnd, CT* V, const int* ldv, const R* tolin, R* work, const int* lwork, CT* zwork, \
+                  const int* lzwrk, int* iwork, const int* liwork, R* option, int* ioption, int* info, CT* parm, int* iparm,     \
+                  size_t, size_t) {                                                                                              \
+    (void)work; (void)lwork; (void)zwork; (void)lzwrk; (void)iwork; (void)liwork;                                                \
+    lansvd_entry<T>(jobu, jobv, *m, *n, k, *kmax, (void*)aprod, U, *ldu, sigma, bnd, V, *ldv, *tolin, option, ioption, info,    \
+                    parm, iparm);                                                                                                \
+  }                                                                                                                              \
+  void P##lansvd_irl_(const char* which, const char* jobu, const char* jobv, const int* m, const int* n, int* dim, const int* p, \
+                      int* neig, const int* maxiter, APT aprod, CT* U, const int* ldu, R* sigma, R* bnd, CT* V, const int* ldv,  \
+                      const R* tolin, R* work, const int* lwork, CT* zwork, const int* lzwrk, int* iwork, const int* liwork,     \
+                      R* option, int* ioption, int* info, CT* parm, int* iparm, size_t, size_t, size_t) {                        \
+    (void)work; (void)lwork; (void)zwork; (void)lzwrk; (void)iwork; (void)liwork;                                                \
+    lansvd_irl_entry<T>(which, jobu, jobv, *m, *n, dim, *p, neig, *maxiter, (void*)aprod, U, *ldu, sigma, bnd, V, *ldv, *tolin,  \
+                        option, ioption, info, parm, iparm);                                                                     \
+  }                                                                                                                              \
+  void P##lanbpro_(const int* m, const int* n, const int* k0, int* k, APT aprod, CT* U, const int* ldu, CT* V, const int* ldv,   \
+                   R* B, const int* ldb, R* rnorm, R* option, int* ioption, R* dwork, CT* zwork, int* iwork, CT* parm,           \
+                   int* iparm, int* ierr) {                                                                                      \
+    (void)dwork; (void)zwork; (void)iwork;                                                                                       \
+    lanbpro_entry<T>(*m, *n, *k0, k, (void*)aprod, U, *ldu, V, *ldv, B, *ldb, rnorm, option, ioption, parm, iparm, ierr);        \
+  }                                                                                                                              \
+  void GEMMNAME(const char* transb, const int* m, const int* n, const int* k, CT* A, const int* lda, const R* B, const int* ldb, \
+                CT* zwork, const int* lzwork, size_t) {                                                                          \
+    (void)zwork; (void)lzwork;                                                                                                   \
+    gemm_ovwr_left_entry<T>(transb, *m, *n, *k, R(1), A, *lda, B, *ldb);                                                         \
+  }
+
+#define PB_COMMON(P, T, R, CT, APT)                                                                                             \
+  void P##reorth_(const int* n, const int* k, const CT* V, const int* ldv, CT* vnew, R* normvnew, const int* index,              \
+                  const R* alpha, CT* work, const int* iflag) {                                                                  \
+    (void)work;                                                                                                                  \
+    reorth_entry<T>(*n, *k, V, *ldv, vnew, normvnew, index, *alpha, *iflag);                                                     \
+  }                                                                                                                              \
+  void P##getu0_(const char* transa, const int* m, const int* n, const int* j, const int* ntry, CT* u0, R* u0norm, const CT* U,  \
+                 const int* ldu, APT aprod, CT* parm, int* iparm, int* ierr, const int* icgs, R* anormest, CT* work, size_t) {   \
+    (void)work;                                                                                                                  \
+    getu0_entry<T>(transa, *m, *n, *j, *ntry, u0, u0norm, U, *ldu, (void*)aprod, parm, iparm, ierr, *icgs, anormest);            \
+  }                                                                                                                              \
+  void P##safescal_(const int* n, const R* alpha, CT* x) { safescal_entry<T>(*n, *alpha, x); }                                   \
+  void propack_b200_aprod_##P##_(const char* transa, const int* m, const int* n, const CT* x, CT* y, CT* parm, int* iparm,       \
+                                 size_t) {                                                                                       \
+    (void)parm;                                                                                                                  \
+    aprod_entry<T>(transa, *m, *n, x, y, iparm);                                                                                 \
+  }                                                                                                                              \
+  int propack_b200_csr_create_##P(int m, int n, const int* rowptr, const int* colind, const CT* values, int index_base) {        \
+    return csr_create<T>(m, n, rowptr, colind, values, index_base);                                                              \
+  }                                                                                                                              \
+  int propack_b200_dense_create_##P(int m, int n, const CT* A, long lda) { return dense_create<T>(m, n, A, lda, false); }
+
+PB_DRIVERS_REAL(s, float, float, pb200_aprod_s_t)
+PB_DRIVERS_REAL(d, double, double, pb200_aprod_d_t)
+PB_DRIVERS_CPLX(c, cplx<float>, float, pb200_complex8, pb200_aprod_c_t, csgemm_ovwr_left_)
+PB_DRIVERS_CPLX(z, cplx<double>, double, pb200_complex16, pb200_aprod_z_t, zdgemm_ovwr_left_)
+PB_COMMON(s, float, float, float, pb200_aprod_s_t)
+PB_COMMON(d, double, double, double, pb200_aprod_d_t)
+PB_COMMON(c, cplx<float>, float, pb200_complex8, pb200_aprod_c_t)
+PB_COMMON(z, cplx<double>, double, pb200_complex16, pb200_aprod_z_t)
+
+// ---- host bidiagonal algebra (real only, as in the reference) -------------------------------------------
+#define PB_HOST_ALG(P, R)                                                                                                       \
+  void P##bsvdstep_(const char* jobu, const char* jobv, const int* m, const int* n, const int* k, const R* sigma, R* D, R* E,    \
+                    R* U, const int* ldu, R* V, const int* ldv, size_t, size_t) {                                                \
+    host::bidiag_shift_sweep<R>(*m, *n, *k, *sigma, D, E, is_yes(jobu) ? U : nullptr, *ldu, is_yes(jobv) ? V : nullptr, *ldv);   \
+  }                                                                                                                              \
+  void P##bdqr_(const int* ignorelast, const char* jobq, const int* n, R* D, R* E, R* c1, R* c2, R* Qt, const int* ldq,          \
+                size_t) {                                                                                                        \
+    host::bidiag_qr<R>(*ignorelast != 0, is_yes(jobq), *n, D, E, *c1, *c2, Qt, *ldq);                                            \
+  }                                                                                                                              \
+  void P##refinebounds_(const int* n, const int* k, const R* theta, R* bound, const R* tol, const R* eps34) {                    \
+    host::refine_bounds<R>(*n, *k, theta, bound, *tol, *eps34);                                                                  \
+  }                                                                                                                              \
+  void P##set_mu_(const int* k, R* mu, const int* index, const R* val) {                                                         \
+    for (int i = 0; index[i] <= *k && index[i] > 0; i += 2)                                                                      \
+      for (int t = index[i]; t <= index[i + 1]; ++t) mu[t - 1] = *val;                                                           \
+  }                                                                                                                              \
+  void P##compute_int_(const R* mu, const int* j, const R* delta, const R* eta, int* index) {                                    \
+    std::vector<R> w(mu, mu + *j);                                                                                               \
+    host::IntervalList idx(2 * *j + 4);                                                                                          \
+    if (*delta < *eta) { host::select_intervals<R>(w, *j, *delta, *eta, idx); return; }                                          \
+    host::select_intervals<R>(w, *j, *delta, *eta, idx);                                                                         \
+    int i = 0;                                                                                                                   \
+    for (;; i += 2) { index[i] = idx.v[i]; if (idx.v[i] > *j || idx.v[i] <= 0) break; index[i + 1] = idx.v[i + 1]; }             \
+  }                                                                                                                              \
+  void P##update_mu_(R* mumax, R* mu, const R* nu, const int* j, const R* alpha, const R* beta, const R* anorm,                  \
+                     const R* eps1) {                                                                                            \
+    host::OmegaRecurrence<R> om;                                                                                                 \
+    om.mu.assign(mu, mu + *j + 1); om.nu.assign(nu, nu + *j + 1);                                                                \
+    *mumax = om.update_mu(*j, alpha, beta, *anorm, *eps1);                                                                       \
+    for (int i = 0; i <= *j; ++i) mu[i] = om.mu[i];                                                                              \
+  }                                                                                                                              \
+  void P##update_nu_(R* numax, const R* mu, R* nu, const int* j, const R* alpha, const R* beta, const R* anorm,                  \
+                     const R* eps1) {                                                                                            \
+    if (*j <= 1) return;                                                                                                         \
+    host::OmegaRecurrence<R> om;                                                                                                 \
+    om.mu.assign(mu, mu + *j + 1); om.nu.assign(nu, nu + *j + 1);                                                                \
+    *numax = om.update_nu(*j, alpha, beta, *anorm, *eps1);                                                                       \
+    for (int i = 0; i < *j; ++i) nu[i] = om.nu[i];                                                                               \
+  }
+PB_HOST_ALG(s, float)
+PB_HOST_ALG(d, double)
+
+void clearstat_(void) {
+  std::memset(&timing_, 0, sizeof timing_);
+  try { Context::get().ctr = Counters(); } catch (...) {}
+}
+void printstat_(void) {  // layout follows double/printstat.F:35-75
+  printf(" +-----------------------------------------------------------+\n");
+  printf(" Dimension of Lanczos basis                  = %12d\n", timing_.nlandim);
+  printf(" Number of singular values requested         = %12d\n", timing_.nsing);
+  printf(" Number of restarts                          = %12d\n", timing_.nrestart);
+  printf(" Number of matrix-vector multiplications     = %12d\n", timing_.nopx);
+  printf(" Number of reorthogonalizations              = %12d\n", timing_.nreorth);
+  printf(" Number of inner products in reorth.         = %12d\n", timing_.ndot);
+  printf(" Number of bidiagonal SVDs calculated        = %12d\n", timing_.nbsvd);
+  printf("\n");
+  printf("  Time spent doing matrix-vector multiply    = %12.4e\n", timing_.tmvopx);
+  printf("  Time spent generating starting vectors     = %12.4e\n", timing_.tgetu0);
+  printf("    Time spent reorthogonalizing             = %12.4e\n", timing_.treorth);
+  printf("  Time spent calculating bidiagonal SVDs     = %12.4e\n", timing_.tbsvd);
+  printf("  Time spent on restarts                     = %12.4e\n", timing_.trestart);
+  printf("  Time spent calculating Ritz vectors        = %12.4e\n", timing_.tritzvec);
+  printf(" +-----------------------------------------------------------+\n");
+}
+
+// ---- operators ------------------------------------------------------------------------------------------
+int propack_b200_dense_adopt_device_d(int m, int n, const double* A_device, long lda) {
+  return dense_create<double>(m, n, A_device, lda, true);
+}
+int propack_b200_op_destroy(int handle) { return g_ops.erase(handle) ? 0 : -1; }
+double propack_b200_op_bytes(int handle, int adjoint) {
+  auto it = g_ops.find(handle);
+  if (it == g_ops.end()) return -1.0;
+  return dispatch(it->second.tag, [&](auto* t) {
+    using T = std::remove_pointer_t<decltype(t)>;
+    return static_cast<LinOp<T>*>(it->second.op.get())->algorithmic_bytes(adjoint != 0);
+  });
+}
+int propack_b200_csr_get_transpose(int handle, int* t_rowptr, int* t_colind, void* t_values) {
+  PB_API_TRY
+  auto it = g_ops.find(handle);
+  if (it == g_ops.end() || it->second.kind != 0) throw std::runtime_error("propack_b200: not a CSR operator handle");
+  return dispatch(it->second.tag, [&](auto* t) {
+    using T = std::remove_pointer_t<decltype(t)>;
+    auto* op = static_cast<CsrOperator<T>*>(it->second.op.get());
+    PB_CUDA(cudaMemcpy(t_rowptr, op->trp.p, sizeof(int) * (op->n + 1), cudaMemcpyDeviceToHost));
+    if (op->A.nnz) {
+      PB_CUDA(cudaMemcpy(t_colind, op->tci.p, sizeof(int) * op->A.nnz, cudaMemcpyDeviceToHost));
+      PB_CUDA(cudaMemcpy(t_values, op->tva.p, sizeof(T) * op->A.nnz, cudaMemcpyDeviceToHost));
+    }
+    return 0;
+  });
+  PB_API_CATCH(return code__)
+}
+
+// ---- solver sessions ----------------------------------------------------------------------------------------
+int propack_b200_solver_create(int op_handle, int ucols, int vcols) {
+  PB_API_TRY
+  auto it = g_ops.find(op_handle);
+  if (it == g_ops.end()) throw std::runtime_error("propack_b200: unknown operator handle");
+  return dispatch(it->second.tag, [&](auto* t) {
+    using T = std::remove_pointer_t<decltype(t)>;
+    return solver_create_t<T>(op_handle, ucols, vcols);
+  });
+  PB_API_CATCH(return code__)
+}
+int propack_b200_solver_destroy(int solver) { return g_solvers.erase(solver) ? 0 : -1; }
+int propack_b200_solver_set_start(int solver, const void* u0_host) {
+  PB_API_TRY
+  SolverEntry& s = find_solver(solver);
+  return dispatch(s.tag, [&](auto* t) {
+    using T = std::remove_pointer_t<decltype(t)>;
+    auto* e = static_cast<Engine<T>*>(s.engine.get());
+    if (u0_host) PB_CUDA(cudaMemcpyAsync(e->U, u0_host, sizeof(T) * e->m, cudaMemcpyHostToDevice, e->c.stream));
+    else PB_CUDA(cudaMemsetAsync(e->U, 0, sizeof(T) * e->ldu, e->c.stream));
+    e->c.sync();
+    return 0;
+  });
+  PB_API_CATCH(return code__)
+}
+int propack_b200_solver_lansvd(int solver, int jobu, int jobv, int* k, int kmax, void* sigma, void* bnd, double tolin, void* option3,
+                               int* ioption, int* info) {
+  PB_API_TRY
+  SolverEntry& s = find_solver(solver);
+  return dispatch(s.tag, [&](auto* t) {
+    using T = std::remove_pointer_t<decltype(t)>;
+    using R = real_t<T>;
+    auto* e = static_cast<Engine<T>*>(s.engine.get());
+    *info = e->lansvd(jobu != 0, jobv != 0, *k, kmax, (R*)sigma, (R*)bnd, (R)tolin, (R*)option3, ioption);
+    e->c.sync();
+    publish_timing(e->c);
+    return 0;
+  });
+  PB_API_CATCH(*info = code__; return code__)
+}
+int propack_b200_solver_lansvd_irl(int solver, int which_smallest, int jobu, int jobv, int* dim, int p, int* neig, int maxiter,
+                                   void* sigma, void* bnd, double tolin, void* option4, int* ioption, int* info) {
+  PB_API_TRY
+  SolverEntry& s = find_solver(solver);
+  return dispatch(s.tag, [&](auto* t) {
+    using T = std::remove_pointer_t<decltype(t)>;
+    using R = real_t<T>;
+    auto* e = static_cast<Engine<T>*>(s.engine.get());
+    *info = e->lansvd_irl(which_smallest != 0, jobu != 0, jobv != 0, *dim, p, *neig, maxiter, (R*)sigma, (R*)bnd, (R)tolin,
+                          (R*)option4, ioption);
+    e->c.sync();
+    publish_timing(e->c);
+    return 0;
+  });
+  PB_API_CATCH(*info = code__; return code__)
+}
+int propack_b200_solver_get_u(int solver, int ncols, void* U_host, long ldu) {
+  PB_API_TRY
+  SolverEntry& s = find_solver(solver);
+  return dispatch(s.tag, [&](auto* t) {
+    using T = std::remove_pointer_t<decltype(t)>;
+    auto* e = static_cast<Engine<T>*>(s.engine.get());
+    download_cols<T>(e->c, U_host, ldu, e->U, e->ldu, e->m, std::min(ncols, e->ucols));
+    e->c.sync();
+    return 0;
+  });
+  PB_API_CATCH(return code__)
+}
+int propack_b200_solver_get_v(int solver, int ncols, void* V_host, long ldv) {
+  PB_API_TRY
+  SolverEntry& s = find_solver(solver);
+  return dispatch(s.tag, [&](auto* t) {
+    using T = std::remove_pointer_t<decltype(t)>;
+    auto* e = static_cast<Engine<T>*>(s.engine.get());
+    download_cols<T>(e->c, V_host, ldv, e->V, e->ldv, e->n, std::min(ncols, e->vcols));
+    e->c.sync();
+    return 0;
+  });
+  PB_API_CATCH(return code__)
+}
+
+// ---- runtime --------------------------------------------------------------------------------------------------
+int propack_b200_init(void) {
+  PB_API_TRY
+  Context::get();
+  host::bind_lapack();
+  return 0;
+  PB_API_CATCH(return code__)
+}
+int propack_b200_set_stream(void* s) {
+  PB_API_TRY
+  Context::get().set_stream((cudaStream_t)s);
+  return 0;
+  PB_API_CATCH(return code__)
+}
+int propack_b200_set_lapack(const char* path) {
+  PB_API_TRY
+  host::bind_lapack(path);
+  return 0;
+  PB_API_CATCH(return code__)
+}
+void propack_b200_set_profile(int on) { try { Context::get().profile = on != 0; } catch (...) {} }
+void propack_b200_reset_counters(void) { try { Context::get().ctr = Counters(); } catch (...) {} }
+void propack_b200_get_counters(long long* out) {
+  std::memset(out, 0, sizeof(long long) * 16);
+  try {
+    const Counters& c = Context::get().ctr;
+    long long v[16] = {c.nopx, c.nreorth, c.ndot, c.nitref, c.nrestart, c.nbsvd, c.nlandim, c.nsing, c.nsteps, c.reorth_passes,
+                       c.reorth_cols, c.reorth_elems, c.reorth_vec_elems, c.launches, c.host_syncs, 0};
+    std::memcpy(out, v, sizeof v);
+  } catch (...) {}
+}
+void propack_b200_get_phase_ms(double* out_ms, long long* out_launches) {
+  try {
+    const Counters& c = Context::get().ctr;
+    for (int i = 0; i < PH_COUNT; ++i) { if (out_ms) out_ms[i] = c.phase_ms[i]; if (out_launches) out_launches[i] = c.phase_launches[i]; }
+  } catch (...) {}
+}
+const char* propack_b200_last_error(void) { return g_last_error.c_str(); }
+int propack_b200_device_sms(void) { try { return Context::get().num_sms; } catch (...) { return -1; } }
+
+}  // extern "C"
+
+// ---- micro-benchmark hooks ------------------------------------------------------------------------------------
+namespace {
+struct L2Flusher {
+  DeviceBuffer<char> buf;
+  void flush(Context& c) {
+    if (!buf.p) buf.alloc(256u << 20);
+    PB_CUDA(cudaMemsetAsync(buf.p, 1, buf.n, c.stream));
+  }
+};
+template <class F> double time_launches(Context& c, int reps, bool flush, F f) {
+  static L2Flusher fl;
+  cudaEvent_t e0, e1;
+  PB_CUDA(cudaEventCreate(&e0)); PB_CUDA(cudaEventCreate(&e1));
+  double total = 0;
+  for (int r = -2; r < reps; ++r) {  // 2 warm-up launches
+    if (flush) fl.flush(c);
+    PB_CUDA(cudaEventRecord(e0, c.stream));
+    f();
+    PB_CUDA(cudaEventRecord(e1, c.stream));
+    PB_CUDA(cudaEventSynchronize(e1));
+    float ms = 0; PB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    if (r >= 0) total += ms;
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  return total / std::max(reps, 1);
+}
+}  // namespace
+
+extern "C" {
+
+double propack_b200_bench_reorth_d(long L, int l, int reps, int flush_l2) {
+  PB_API_TRY
+  Context& c = Context::get();
+  const long ld = Engine<double>::pad_ld(L);
+  DeviceBuffer<double> V((size_t)ld * l), q(ld), h(l + 8);
+  PB_CUDA(cudaMemsetAsync(V.p, 0, sizeof(double) * V.n, c.stream));
+  PB_CUDA(cudaMemsetAsync(q.p, 0, sizeof(double) * q.n, c.stream));
+  int iseed[4] = {1, 3, 5, 7};
+  Pending p;
+  for (int j = 0; j < l; ++j) { iseed[3] = 2 * j + 1; k_larnv_nrm<double>(c, L, V.p + (size_t)j * ld, iseed, &p); }
+  iseed[2] = 77; k_larnv_nrm<double>(c, L, q.p, iseed, &p);
+  c.wait(p);
+  k_scal<double>(c, (long)ld * l, V.p, 1.0 / std::sqrt((double)L));  // keep q bounded over repeated passes
+  return time_launches(c, reps, flush_l2 != 0, [&] {
+    Pending pn;
+    k_gemv_t<double>(c, L, l, V.p, ld, q.p, h.p);
+    k_gemv_n<double>(c, L, l, V.p, ld, h.p, 1.0, q.p, -1, q.p, &pn);
+  });
+  PB_API_CATCH(return (double)code__)
+}
+double propack_b200_bench_spmv(int op_handle, int adjoint, int reps, int flush_l2) {
+  PB_API_TRY
+  Context& c = Context::get();
+  auto it = g_ops.find(op_handle);
+  if (it == g_ops.end()) throw std::runtime_error("propack_b200: unknown operator handle");
+  return dispatch(it->second.tag, [&](auto* t) {
+    using T = std::remove_pointer_t<decltype(t)>;
+    LinOp<T>* op = static_cast<LinOp<T>*>(it->second.op.get());
+    const long nx = adjoint ? op->m : op->n, ny = adjoint ? op->n : op->m;
+    DeviceBuffer<T> x(Engine<T>::pad_ld(nx)), y(Engine<T>::pad_ld(ny)), prev(Engine<T>::pad_ld(ny));
+    PB_CUDA(cudaMemsetAsync(x.p, 0, sizeof(T) * x.n, c.stream));
+    PB_CUDA(cudaMemsetAsync(y.p, 0, sizeof(T) * y.n, c.stream));
+    PB_CUDA(cudaMemsetAsync(prev.p, 0, sizeof(T) * prev.n, c.stream));
+    int iseed[4] = {1, 3, 5, 7};
+    Pending p;
+    k_larnv_nrm<T>(c, nx, x.p, iseed, &p);
+    iseed[0] = 9; k_larnv_nrm<T>(c, ny, prev.p, iseed, &p);
+    c.wait(p);
+    return time_launches(c, reps, flush_l2 != 0, [&] {
+      Pending pn;
+      op->apply(c, adjoint != 0, x.p, y.p, real_t<T>(-0.5), prev.p, &pn);
+    });
+  });
+  PB_API_CATCH(return (double)code__)
+}
+double propack_b200_bench_gemm_d(long M, int N, int K, int reps) {
+  PB_API_TRY
+  Context& c = Context::get();
+  const long ld = Engine<double>::pad_ld(M);
+  DeviceBuffer<double> A((size_t)ld * K);
+  PB_CUDA(cudaMemsetAsync(A.p, 0, sizeof(double) * A.n, c.stream));
+  int iseed[4] = {1, 3, 5, 7};
+  Pending p;
+  for (int j = 0; j < K; ++j) { iseed[3] = 2 * j + 1; k_larnv_nrm<double>(c, M, A.p + (size_t)j * ld, iseed, &p); }
+  c.wait(p);
+  std::vector<double> W((size_t)K * N);
+  for (size_t i = 0; i < W.size(); ++i) W[i] = ((i * 2654435761u) % 1000) / 1000.0 / K;
+  return time_launches(c, reps, false, [&] { k_gemm_tall<double>(c, M, N, K, A.p, ld, W.data()); });
+  PB_API_CATCH(return (double)code__)
+}
+
+}  // extern "C"

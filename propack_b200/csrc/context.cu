@@ -1,0 +1,98 @@
+#include "context.hpp"
+
+#include <cstdlib>
+#include <cstring>
+
+namespace pb {
+
+Context& Context::get() {
+  static Context* ctx = new Context();  // leaked on purpose: CUDA teardown order at exit is undefined
+  return *ctx;
+}
+
+Context::Context() {
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    throw CudaError(e == cudaSuccess ? cudaErrorNoDevice : e,
+                    "propack_b200: no CUDA device available -- this library has no CPU fallback");
+  PB_CUDA(cudaGetDevice(&device));
+  cudaDeviceProp prop;
+  PB_CUDA(cudaGetDeviceProperties(&prop, device));
+  num_sms = prop.multiProcessorCount;
+  if (prop.major < 10 && !std::getenv("PROPACK_B200_ALLOW_ANY_ARCH")) {
+    char buf[256];
+    snprintf(buf, sizeof buf, "propack_b200: device '%s' is sm_%d%d; this build targets sm_100a (B200) only", prop.name,
+             prop.major, prop.minor);
+    throw CudaError(cudaErrorInvalidDevice, buf);
+  }
+  PB_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+  PB_CUDA(cudaHostAlloc((void**)&host_slots, sizeof(ScalarSlot) * kSlots, cudaHostAllocMapped));
+  std::memset((void*)host_slots, 0, sizeof(ScalarSlot) * kSlots);
+  PB_CUDA(cudaHostGetDevicePointer((void**)&host_slots_dev, (void*)host_slots, 0));
+  PB_CUDA(cudaMalloc((void**)&dev_slots, sizeof(ScalarSlot) * kSlots));
+  PB_CUDA(cudaMemset(dev_slots, 0, sizeof(ScalarSlot) * kSlots));
+  PB_CUDA(cudaMalloc((void**)&partials, sizeof(double) * 2 * kMaxCtas));
+  PB_CUDA(cudaMalloc((void**)&ticket, sizeof(unsigned int)));
+  PB_CUDA(cudaMemset(ticket, 0, sizeof(unsigned int)));
+  PB_CUDA(cudaDeviceSynchronize());
+  profile = std::getenv("PROPACK_B200_PROFILE") != nullptr;
+}
+
+void Context::set_stream(cudaStream_t s) {
+  PB_CUDA(cudaStreamSynchronize(stream));
+  if (owns_stream && stream) cudaStreamDestroy(stream);
+  stream = s;
+  owns_stream = false;
+}
+
+double Context::wait(const Pending& p, double* imag) {
+  volatile ScalarSlot* s = host_slots + p.slot;
+  ctr.host_syncs += 1;
+  unsigned long spins = 0;
+  while (s->seq != p.seq) {
+    if ((++spins & 0xfffu) == 0) {
+      cudaError_t e = cudaStreamQuery(stream);
+      if (e == cudaSuccess) {
+        // stream drained: the value must be there now (the kernel's system-scope fence precedes completion)
+        if (s->seq == p.seq) break;
+        throw CudaError(cudaErrorUnknown, "propack_b200: reduction result was never published (internal error)");
+      }
+      if (e != cudaErrorNotReady) cuda_check(e, "cudaStreamQuery while waiting for a scalar", __FILE__, __LINE__);
+    }
+  }
+  if (imag) *imag = s->im;
+  return s->re;
+}
+
+void* Context::scratch(size_t bytes) {
+  if (bytes > scratch_bytes_) {
+    if (scratch_) { PB_CUDA(cudaStreamSynchronize(stream)); cudaFree(scratch_); }
+    size_t want = bytes + bytes / 2 + 4096;
+    PB_CUDA(cudaMalloc(&scratch_, want));
+    scratch_bytes_ = want;
+  }
+  return scratch_;
+}
+
+Context::PhaseScope::PhaseScope(Context& c_, Phase p) : c(c_), ph(p), l0(c_.ctr.launches) {
+  if (c.profile) {
+    PB_CUDA(cudaEventCreate(&e0));
+    PB_CUDA(cudaEventCreate(&e1));
+    PB_CUDA(cudaEventRecord(e0, c.stream));
+  }
+}
+Context::PhaseScope::~PhaseScope() {
+  c.ctr.phase_launches[ph] += c.ctr.launches - l0;
+  if (c.profile) {
+    cudaEventRecord(e1, c.stream);
+    cudaEventSynchronize(e1);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    c.ctr.phase_ms[ph] += ms;
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+  }
+}
+
+}  // namespace pb

@@ -1,0 +1,103 @@
+// propack_b200 -- per-process device context: stream, scalar slots, reduction workspace,
+// phase timers.  One context per process (one process per GPU).
+#pragma once
+#include <chrono>
+#include <vector>
+
+#include "common.cuh"
+
+namespace pb {
+
+// Phases timed with CUDA events on the library stream (the reference's dead `tmvopx treorth
+// tritzvec ...` timers of stat.h:9-15, made live).  Only filled when profiling is enabled.
+enum Phase { PH_APROD = 0, PH_REORTH, PH_LEVEL1, PH_GETU0, PH_RITZ, PH_RESTART, PH_HOST_BSVD, PH_COUNT };
+
+struct Counters {  // COMMON /timing/ integer counters (stat.h:7-8) + byte model inputs
+  long long nopx = 0, nreorth = 0, ndot = 0, nitref = 0, nrestart = 0, nbsvd = 0, nlandim = 0, nsing = 0;
+  long long nsteps = 0;        // Lanczos steps (dlanbpro.F:283 loop iterations)
+  long long reorth_passes = 0; // GS passes executed
+  long long reorth_cols = 0;   // sum over passes of columns swept
+  long long reorth_elems = 0;  // sum over passes of L * l  (for the byte model  w*L*(2l+3))
+  long long reorth_vec_elems = 0;  // sum over passes of L
+  long long launches = 0;      // kernels launched by this library
+  long long host_syncs = 0;    // scalar read-backs the host waited on
+  double phase_ms[PH_COUNT] = {0, 0, 0, 0, 0, 0, 0};
+  long long phase_launches[PH_COUNT] = {0, 0, 0, 0, 0, 0, 0};
+};
+
+class Context {
+ public:
+  static Context& get();       // lazily created on the current device
+  cudaStream_t stream = nullptr;
+  bool owns_stream = true;
+  int device = 0;
+  int num_sms = 148;
+  Counters ctr;
+  bool profile = false;        // per-phase CUDA-event timing (adds syncs; off for benchmarks)
+
+  // --- scalar slots -------------------------------------------------------------------------
+  static constexpr int kSlots = 64;
+  ScalarSlot* host_slots = nullptr;      // pinned + mapped
+  ScalarSlot* host_slots_dev = nullptr;  // device view of the same memory
+  ScalarSlot* dev_slots = nullptr;
+  double* partials = nullptr;
+  unsigned int* ticket = nullptr;
+  unsigned long long seq = 0;
+  int next_slot = 0;
+
+  struct Pending { int slot; unsigned long long seq; };
+  // Allocate a result slot for the next reducing kernel.
+  ReduceWs new_reduce(Pending* p) {
+    int s = next_slot; next_slot = (next_slot + 1) % kSlots;
+    ReduceWs ws;
+    ws.partials = partials; ws.ticket = ticket;
+    ws.dev_slot = dev_slots + s; ws.host_slot = host_slots_dev + s; ws.seq = ++seq;
+    p->slot = s; p->seq = ws.seq;
+    return ws;
+  }
+  const ScalarSlot* dev_slot(const Pending& p) const { return dev_slots + p.slot; }
+  // Spin until the kernel that owns `p` has published; returns the real part (imag via out param).
+  double wait(const Pending& p, double* imag = nullptr);
+
+  void set_stream(cudaStream_t s);
+  void sync() { PB_CUDA(cudaStreamSynchronize(stream)); }
+  int grid_for(long work_items, int per_cta, int ctas_per_sm) const {
+    long need = (work_items + per_cta - 1) / per_cta;
+    long cap = (long)num_sms * ctas_per_sm;
+    if (cap > kMaxCtas) cap = kMaxCtas;
+    if (need < 1) need = 1;
+    return (int)(need < cap ? need : cap);
+  }
+
+  // --- phase timing ---------------------------------------------------------------------------
+  struct PhaseScope {
+    Context& c; Phase ph; cudaEvent_t e0 = nullptr, e1 = nullptr; long long l0;
+    PhaseScope(Context& c_, Phase p);
+    ~PhaseScope();
+  };
+
+  // scratch device buffer that grows on demand (coefficients, partials of gemv_t, ...)
+  void* scratch(size_t bytes);
+
+ private:
+  Context();
+  void* scratch_ = nullptr;
+  size_t scratch_bytes_ = 0;
+};
+
+template <class T> struct DeviceBuffer {
+  T* p = nullptr; size_t n = 0;
+  DeviceBuffer() {}
+  explicit DeviceBuffer(size_t n_) { alloc(n_); }
+  DeviceBuffer(const DeviceBuffer&) = delete;
+  DeviceBuffer& operator=(const DeviceBuffer&) = delete;
+  void alloc(size_t n_) {
+    free();
+    n = n_;
+    if (n) PB_CUDA(cudaMalloc((void**)&p, n * sizeof(T)));
+  }
+  void free() { if (p) cudaFree(p); p = nullptr; n = 0; }
+  ~DeviceBuffer() { free(); }
+};
+
+}  // namespace pb

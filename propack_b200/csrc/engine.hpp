@@ -1,0 +1,261 @@
+// propack_b200 -- device-resident Lanczos bidiagonalisation engine (host control flow).
+//
+// Mirrors the reference's call tree  xLANSVD / xLANSVD_IRL -> xLANBPRO -> {APROD, xREORTH,
+// xGETU0, xSAFESCAL} and xRITZVEC -> xGEMM_OVWR_LEFT  (SURVEY.md section 3), but the Lanczos bases U, V and
+// the operator live in HBM for the whole solve: the host only sees the scalars the algorithm
+// branches on (alpha, beta, dot products, norms) and the O(k) recurrences / O(k^2) bidiagonal
+// problem.  There is no CPU fallback: every vector operation below is a CUDA kernel launch.
+#pragma once
+#include <cmath>
+#include <functional>
+#include <memory>
+#include <stdexcept>
+#include <vector>
+
+#include "context.hpp"
+#include "host_algebra.hpp"
+#include "host_lapack.hpp"
+#include "kernels.cuh"
+
+namespace pb {
+
+// Fortran-ABI user APROD (dlansvd.F:23-31): hidden CHARACTER length appended by value.
+template <class T>
+using aprod_f77_t = void (*)(const char* transa, const int* m, const int* n, const T* x, T* y, void* parm, int* iparm,
+                             size_t transa_len);
+
+inline void set_scalar(float& s, double re, double) { s = (float)re; }
+inline void set_scalar(double& s, double re, double) { s = re; }
+template <class R> inline void set_scalar(cplx<R>& s, double re, double im) { s = cplx<R>((R)re, (R)im); }
+inline float neg(float a) { return -a; }
+inline double neg(double a) { return -a; }
+template <class R> inline cplx<R> neg(cplx<R> a) { return cplx<R>(-a.x, -a.y); }
+
+// ------------------------------------------------------------------------------------------------
+// Linear operators.  apply(): y = op(A) x + coef*prev (prev may be null), optional ||y|| publication.
+// ------------------------------------------------------------------------------------------------
+template <class T> struct LinOp {
+  using R = real_t<T>;
+  int m = 0, n = 0;
+  virtual ~LinOp() {}
+  virtual void apply(Context& c, bool adjoint, const T* x, T* y, R coef, const T* prev, Pending* nrm) = 0;
+  virtual double algorithmic_bytes(bool adjoint) const = 0;  // per apply, SURVEY 8d byte model
+};
+
+template <class T> struct CsrOperator : LinOp<T> {
+  using R = real_t<T>;
+  DeviceBuffer<int> rp, ci, trp, tci, bins, tbins;
+  DeviceBuffer<T> va, tva;
+  CsrDevice<T> A, At;  // At = CSR of A^T (values not conjugated)
+  void apply(Context& c, bool adjoint, const T* x, T* y, R coef, const T* prev, Pending* nrm) override {
+    if (adjoint) k_spmv<T>(c, At, /*conj=*/true, x, y, coef, prev, nrm);
+    else k_spmv<T>(c, A, false, x, y, coef, prev, nrm);
+  }
+  double algorithmic_bytes(bool adjoint) const override {
+    const double w = sizeof(T);
+    const double rows = adjoint ? this->n : this->m, cols = adjoint ? this->m : this->n;
+    return (double)A.nnz * (w + 4) + (rows + 1) * 4 + cols * w + rows * w;
+  }
+};
+
+// Dense column-major operator (BASELINE config 3): both products are the reorthogonalisation
+// GEMV kernels over A itself.
+template <class T> struct DenseOperator : LinOp<T> {
+  using R = real_t<T>;
+  DeviceBuffer<T> store;
+  const T* A = nullptr; long lda = 0;
+  void apply(Context& c, bool adjoint, const T* x, T* y, R coef, const T* prev, Pending* nrm) override {
+    if (adjoint) {
+      k_gemv_t<T>(c, this->m, this->n, A, lda, x, y);
+      if (prev) k_axpy_nrm<T>(c, this->n, T(coef), prev, y, nrm ? nrm : &scratch_p);
+      else if (nrm) k_nrm2<T>(c, this->n, y, nrm);
+    } else {
+      k_gemv_n<T>(c, this->m, this->n, A, lda, x, coef, prev, +1, y, nrm);
+    }
+  }
+  double algorithmic_bytes(bool) const override { return (double)this->m * this->n * sizeof(T); }
+  Pending scratch_p{};
+};
+
+// Generic user callback: host-staged (D2H x, call, H2D y).  Correct, PCIe-bound; the fast path is a
+// built-in operator handle.
+template <class T> struct CallbackOperator : LinOp<T> {
+  using R = real_t<T>;
+  aprod_f77_t<T> fn = nullptr; void* parm = nullptr; int* iparm = nullptr;
+  std::vector<T> hx, hy;
+  void apply(Context& c, bool adjoint, const T* x, T* y, R coef, const T* prev, Pending* nrm) override {
+    const int nx = adjoint ? this->m : this->n, ny = adjoint ? this->n : this->m;
+    hx.resize(nx); hy.resize(ny);
+    PB_CUDA(cudaMemcpyAsync(hx.data(), x, sizeof(T) * nx, cudaMemcpyDeviceToHost, c.stream));
+    PB_CUDA(cudaStreamSynchronize(c.stream));
+    const char t = adjoint ? (scalar_traits<T>::is_complex ? 'c' : 't') : 'n';
+    fn(&t, &this->m, &this->n, hx.data(), hy.data(), parm, iparm, 1);
+    PB_CUDA(cudaMemcpyAsync(y, hy.data(), sizeof(T) * ny, cudaMemcpyHostToDevice, c.stream));
+    PB_CUDA(cudaStreamSynchronize(c.stream));
+    if (prev) k_axpy_nrm<T>(c, ny, T(coef), prev, y, nrm ? nrm : &scratch_p);
+    else if (nrm) k_nrm2<T>(c, ny, y, nrm);
+  }
+  double algorithmic_bytes(bool) const override { return 0.0; }
+  Pending scratch_p{};
+};
+
+// ------------------------------------------------------------------------------------------------
+// Engine
+// ------------------------------------------------------------------------------------------------
+template <class T> class Engine {
+ public:
+  using R = real_t<T>;
+  Context& c;
+  LinOp<T>* op;
+  int m, n;
+  long ldu, ldv;      // padded leading dimensions (multiples of 32 elements => 256-byte aligned columns)
+  int ucols, vcols;   // allocated columns
+  DeviceBuffer<T> Ubuf, Vbuf, wrk, hbuf;
+  T* U; T* V;
+
+  static long pad_ld(long rows) { return (rows + 31) / 32 * 32; }
+
+  Engine(Context& ctx, LinOp<T>* op_, int ucols_, int vcols_)
+      : c(ctx), op(op_), m(op_->m), n(op_->n), ldu(pad_ld(op_->m)), ldv(pad_ld(op_->n)), ucols(ucols_), vcols(vcols_) {
+    Ubuf.alloc((size_t)ldu * ucols);
+    Vbuf.alloc((size_t)ldv * vcols);
+    wrk.alloc((size_t)std::max(ldu, ldv));
+    hbuf.alloc((size_t)std::max(ucols, vcols) + 8);
+    U = Ubuf.p; V = Vbuf.p;
+    // padding rows must be (and stay) zero: kernels read whole 128-bit packs past the last row
+    PB_CUDA(cudaMemsetAsync(U, 0, sizeof(T) * (size_t)ldu * ucols, c.stream));
+    PB_CUDA(cudaMemsetAsync(V, 0, sizeof(T) * (size_t)ldv * vcols, c.stream));
+    PB_CUDA(cudaMemsetAsync(wrk.p, 0, sizeof(T) * wrk.n, c.stream));
+  }
+  T* ucol(int j) { return U + (size_t)(j - 1) * ldu; }  // 1-based column
+  T* vcol(int j) { return V + (size_t)(j - 1) * ldv; }
+
+  // --- dsafescal (dsafescal.F:4-55) ---------------------------------------------------------------
+  void safescal(long len, R alpha, T* x) {
+    Context::PhaseScope ps(c, PH_LEVEL1);
+    const R sfmin = host::Machine<R>::sfmin;
+    if (std::fabs(alpha) >= sfmin) { k_scal<T>(c, len, x, R(1) / alpha); return; }
+    // dlascl('General',..,cfrom=alpha,cto=1): multiply in safe steps (Lapack_Util/dlascl.f:113-137)
+    const R smlnum = sfmin, bignum = R(1) / smlnum;
+    R cfromc = alpha, ctoc = 1;
+    for (bool done = false; !done;) {
+      const R cfrom1 = cfromc * smlnum, cto1 = ctoc / bignum;
+      R mul;
+      if (std::fabs(cfrom1) > std::fabs(ctoc) && ctoc != R(0)) { mul = smlnum; cfromc = cfrom1; }
+      else if (std::fabs(cto1) > std::fabs(cfromc)) { mul = bignum; ctoc = cto1; }
+      else { mul = ctoc / cfromc; done = true; }
+      k_scal<T>(c, len, x, mul);
+    }
+  }
+
+  R nrm2(long len, const T* x) {
+    Pending p; k_nrm2<T>(c, len, x, &p);
+    return (R)c.wait(p);
+  }
+
+  // --- dreorth (dreorth.F:5-101) ----------------------------------------------------------------------
+  // Iterated Gram-Schmidt of vnew against basis(:, intervals), DGKS test with factor `kappa`, at most
+  // NTRY = 5 passes, else the vector is declared in span(basis) and zeroed.  Each interval is one GEMV
+  // pair (dcgs, dreorth.F:106-210); intervals are swept in order, as the reference's block loop does.
+  // iflag (CGS=1 / MGS=0) selects the same kernels: on this hardware column-sequential MGS
+  // (dmgs.risc.F:58-79) would be l dependent grid-wide reductions, so it is realised as the blocked
+  // GEMV pair with DGKS re-iteration, which meets the same orthogonality test.
+  void reorth(long len, int k, const T* basis, long ld, T* vnew, R& normvnew, const host::IntervalList& idx, R kappa,
+              int iflag) {
+    (void)iflag;
+    if (k <= 0 || len <= 0) return;
+    Context::PhaseScope ps(c, PH_REORTH);
+    const int NTRY = 5;
+    for (int itry = 0; itry < NTRY; ++itry) {
+      const R norm0 = normvnew;
+      Pending p;
+      bool published = false;
+      int count = 0;
+      idx.for_each(k, [&](int, int) { ++count; });
+      int seen = 0;
+      idx.for_each(k, [&](int pcol, int qcol) {
+        ++seen;
+        const int l = qcol - pcol + 1;
+        c.ctr.ndot += l;
+        if (l <= 0) return;
+        const T* blk = basis + (size_t)(pcol - 1) * ld;
+        k_gemv_t<T>(c, len, l, blk, ld, vnew, hbuf.p);
+        reduce_coefficients(l);
+        const bool last = (seen == count);
+        k_gemv_n<T>(c, len, l, blk, ld, hbuf.p, R(1), vnew, -1, vnew, last ? &p : nullptr);
+        if (last) published = true;
+        c.ctr.reorth_cols += l;
+        c.ctr.reorth_elems += (long long)l * len;
+        c.ctr.reorth_vec_elems += len;
+      });
+      c.ctr.reorth_passes += 1;
+      c.ctr.ndot += k;
+      if (!published) k_nrm2<T>(c, len, vnew, &p);
+      normvnew = (R)c.wait(p);
+      if (normvnew > kappa * norm0) { c.ctr.nreorth += 1; return; }
+    }
+    normvnew = 0;
+    k_zero<T>(c, len, vnew);
+    c.ctr.nreorth += 1;
+  }
+  // hook for the row-sharded multi-GPU build: all-reduce of the l coefficients
+  std::function<void(T*, int)> allreduce_coeffs;
+  void reduce_coefficients(int l) { if (allreduce_coeffs) allreduce_coeffs(hbuf.p, l); }
+
+  // --- dgetu0 (dgetu0.F:11-89) ---------------------------------------------------------------------------
+  // u0 <- op(A) r, r ~ LAPACK uniform(-1,1) stream from iseed (1,3,5,7) (reset on every call), then
+  // orthogonalised against basis(:,1:j).  adjoint=false: u0 is an m-vector.
+  void getu0(bool adjoint, int j, int ntry, T* u0, R& u0norm, const T* basis, long ld, int& ierr, int icgs, R& anormest) {
+    Context::PhaseScope ps(c, PH_GETU0);
+    const R kappa = R(0.717f);  // single-precision literal in dgetu0.F:28-29
+    const long rsize = adjoint ? m : n, usize = adjoint ? n : m;
+    int iseed[4] = {1, 3, 5, 7};
+    ierr = 0;
+    for (int itry = 0; itry < ntry; ++itry) {
+      // stream position: itry-th block of rsize values (dlarnv keeps advancing iseed between tries)
+      Pending pr, pu;
+      advance_and_draw(iseed, rsize, wrk.p, &pr);
+      const R nrm = (R)c.wait(pr);
+      op->apply(c, adjoint, wrk.p, u0, R(0), nullptr, &pu);
+      c.ctr.nopx += 1;
+      u0norm = (R)c.wait(pu);
+      anormest = u0norm / nrm;
+      if (j >= 1) {
+        host::IntervalList idx(4);
+        idx.set_single(1, j, j + 1);
+        reorth(usize, j, basis, ld, u0, u0norm, idx, kappa, icgs);
+      }
+      if (u0norm > 0) return;
+    }
+    ierr = -1;
+  }
+  // draw `len` values starting at the current seed and advance the seed past them, like xLARNV
+  void advance_and_draw(int iseed[4], long len, T* x, Pending* p) {
+    k_larnv_nrm<T>(c, len, x, iseed, p);
+    const unsigned long long M = (1ull << 48) - 1;
+    unsigned long long s = ((unsigned long long)iseed[0] << 36) | ((unsigned long long)iseed[1] << 24) |
+                           ((unsigned long long)iseed[2] << 12) | (unsigned long long)iseed[3];
+    unsigned long long e = (unsigned long long)len * (scalar_traits<T>::is_complex ? 2 : 1), base = 33952834046453ull, r = 1;
+    while (e) { if (e & 1) r = (r * base) & M; base = (base * base) & M; e >>= 1; }
+    s = (s * r) & M;
+    iseed[0] = int((s >> 36) & 4095); iseed[1] = int((s >> 24) & 4095); iseed[2] = int((s >> 12) & 4095); iseed[3] = int(s & 4095);
+  }
+
+  // --- dlanbpro (dlanbpro.F:1-549) ----------------------------------------------------------------------
+  // a = B(:,1) (alpha), b = B(:,2) (beta): host arrays of length >= k.  Returns ierr.
+  int lanbpro(int k0, int& k, R* a, R* b, R& rnorm, R* doption, const int* ioption);
+
+  // --- dritzvec (dritzvec.F:1-199) -------------------------------------------------------------------------
+  void ritzvec(bool smallest, bool jobu, bool jobv, int k, int dim, R* D, R* E);
+
+  // --- drivers ------------------------------------------------------------------------------------------
+  // dlansvd (dlansvd.F:1-291); U(:,1) on device holds the start vector (zero => random).  Returns info.
+  int lansvd(bool jobu, bool jobv, int& k, int kmax, R* sigma, R* bnd, R tolin, R* doption, const int* ioption);
+  // dlansvd_irl (dlansvd_irl.F:1-419)
+  int lansvd_irl(bool smallest, bool jobu, bool jobv, int& dim, int p, int& neig, int maxiter, R* sigma, R* bnd, R tolin,
+                 R* doption, const int* ioption);
+};
+
+}  // namespace pb
+
+#include "engine_impl.hpp"

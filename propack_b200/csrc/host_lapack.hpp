@@ -1,0 +1,24 @@
+// propack_b200 -- host LAPACK for the O(k^2) bidiagonal SVD that stays on the CPU
+// (reference: dbdsqr call at double/dlansvd.F:198 / dlansvd_irl.F:228, dbdsdc at dritzvec.F:123;
+// upstream vendors LAPACK 3.0 under */Lapack_Util, here the image's LAPACK is bound at run time).
+#pragma once
+#include <cstddef>
+
+namespace pb {
+namespace host {
+
+// Binds xBDSQR / xBDSDC from a shared object.  Search order: explicit path argument,
+// $PROPACK_B200_LAPACK, liblapack.so.3, libopenblas.so.0, then a scipy_openblas found next to the
+// running Python's scipy (symbols carry a "scipy_" prefix there).  Throws std::runtime_error.
+void bind_lapack(const char* path = nullptr);
+bool lapack_bound();
+
+// singular values of an upper bidiagonal + one row-vector of left rotations (nru = 1)
+void bdsqr_row(int n, double* d, double* e, double* urow, int* info);
+void bdsqr_row(int n, float* d, float* e, float* urow, int* info);
+// divide & conquer SVD of an upper bidiagonal: B = U diag(d) VT  (compq = 'I')
+void bdsdc_full(int n, double* d, double* e, double* U, int ldu, double* VT, int ldvt, int* info);
+void bdsdc_full(int n, float* d, float* e, float* U, int ldu, float* VT, int ldvt, int* info);
+
+}  // namespace host
+}  // namespace pb

@@ -1,0 +1,60 @@
+// propack_b200 -- launch wrappers of the hand-written sm_100a kernels (declarations).
+// Each wrapper enqueues on Context::stream and never synchronises; results the host must branch
+// on come back through Context::Pending slots (see common.cuh).
+#pragma once
+#include "common.cuh"
+#include "context.hpp"
+
+namespace pb {
+
+using Pending = Context::Pending;
+
+// --- level-1 (reference: blasext, double/dblasext.F:6-255; dsafescal.F) ---------------------------
+// x <- a * x                                                     (pdscal dblasext.F:38)
+template <class T> void k_scal(Context& c, long n, T* x, real_t<T> a);
+// x <- x / (*slot).re, scalar taken from a device-resident result slot (speculative dsafescal)
+template <class T> void k_scal_inv_slot(Context& c, long n, T* x, const ScalarSlot* slot);
+// y <- y + a*x ; publish ||y||_2                                  (pdaxpy + pdnrm2 fused, dlanbpro.F:295-296)
+template <class T> void k_axpy_nrm(Context& c, long n, T a, const T* x, T* y, Pending* nrm);
+// publish conj(x).y                                              (pddot dblasext.F:121 / pzdotc)
+template <class T> void k_dotc(Context& c, long n, const T* x, const T* y, Pending* out);
+// publish ||x||_2                                                (pdnrm2 dblasext.F:6)
+template <class T> void k_nrm2(Context& c, long n, const T* x, Pending* out);
+template <class T> void k_zero(Context& c, long n, T* x);          // pdzero dblasext.F:202
+// x(i) <- LAPACK xLARNV(idist=2, iseed) stream element i, i=0..n-1 ; publish ||x||  (dgetu0.F:69-70)
+template <class T> void k_larnv_nrm(Context& c, long n, T* x, const int iseed[4], Pending* nrm);
+
+// --- tall-skinny GEMV pair (reference: dcgs, double/dreorth.F:174 and :199-205) --------------------
+// h(0:l) <- V(:,0:l)^H q   (column-major V, leading dim ldv, L rows).  h is a device buffer.
+template <class T> void k_gemv_t(Context& c, long L, int l, const T* V, long ldv, const T* q, T* h);
+// out <- cin*in + sgn * V(:,0:l) h ; optionally publish ||out||_2.  `in` may alias `out` or be null (cin ignored).
+template <class T>
+void k_gemv_n(Context& c, long L, int l, const T* V, long ldv, const T* h, real_t<T> cin, const T* in, int sgn, T* out,
+              Pending* nrm);
+
+// --- CSR SpMV (reference: the user's APROD, dlansvd.F:20-33; call sites dlanbpro.F:288,420) --------
+template <class T> struct CsrDevice {
+  int rows = 0, cols = 0;
+  long nnz = 0;
+  const int* rp = nullptr;     // [rows+1]
+  const int* ci = nullptr;     // [nnz], sorted within a row
+  const T* va = nullptr;       // [nnz]
+  int lanes_per_row = 8;       // LPR: sub-warp width chosen from the mean row length
+  // row bins (csr_analyze): short rows (<= 4*LPR nnz) are found by scanning all rows;
+  // medium (<= kCsrLongRow nnz) and long rows are listed explicitly.
+  int n_med = 0;
+  const int* med_rows = nullptr;
+  int n_long = 0;
+  const int* long_rows = nullptr;
+};
+constexpr int kCsrLongRow = 2048;
+// y <- op(A) x + coef*prev (prev may be null) ; optionally publish ||y||_2.  conj: use conj(values).
+template <class T>
+void k_spmv(Context& c, const CsrDevice<T>& A, bool conj, const T* x, T* y, real_t<T> coef, const T* prev, Pending* nrm);
+
+// --- tall in-place GEMM (reference: dgemm_ovwr_left, double/dgemm_ovwr.F:56-87) --------------------
+// A(:,0:N) <- A(:,0:K) * W,  W real K x N column-major (ld = K) in HOST memory (it comes from the host
+// bidiagonal SVD); it is packed into DMMA fragment order and uploaded by the wrapper.
+template <class T> void k_gemm_tall(Context& c, long M, int N, int K, T* A, long lda, const real_t<T>* W);
+
+}  // namespace pb

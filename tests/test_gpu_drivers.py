@@ -1,0 +1,257 @@
+"""GPU: driver-level parity -- xLANSVD / xLANSVD_IRL / xLANBPRO through the Fortran C-ABI against the
+oracle, the committed golden vectors (dense LAPACK SVD + SciPy's PROPACK translation of the same inputs)
+and the residual / orthogonality properties the north star names."""
+import os
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+from conftest import DTYPES, GOLDEN, TOL, rand_sparse
+
+pytestmark = pytest.mark.gpu
+
+
+def relerr(a, b):
+    return float(np.max(np.abs(np.asarray(a) - np.asarray(b)) / np.abs(np.asarray(b))))
+
+
+def subspace_dist(X, Y):
+    """max principal-angle sine between equal-dimension subspaces with orthonormal columns (sign/phase free)."""
+    s = np.linalg.svd(X.conj().T @ Y, compute_uv=False)
+    return float(np.sqrt(max(0.0, 1.0 - min(s) ** 2)))
+
+
+def check_triplets(A, r, tol, dtype):
+    U, S, V = r["U"], r["sigma"], r["V"]
+    k = S.size
+    eps = np.finfo(dtype).eps
+    AH = A.conj().T
+    assert np.max(np.linalg.norm(A @ V - U * S, axis=0)) < max(tol, 1e3 * eps) * S[0] * 10
+    assert np.max(np.linalg.norm(AH @ U - V * S, axis=0)) < max(np.sqrt(tol), 1e3 * eps) * S[0] * 10
+    assert np.max(np.abs(U.conj().T @ U - np.eye(k))) < 200 * np.sqrt(eps)
+    assert np.max(np.abs(V.conj().T @ V - np.eye(k))) < 200 * np.sqrt(eps)
+
+
+@pytest.mark.parametrize("cgs", [0, 1])
+def test_illc1850_lansvd_k10(oracle, examples, cgs):
+    """BASELINE config 1: illc1850, k=10, DLANSVD non-restarted."""
+    from propack_b200 import f77
+    import propack_b200
+    g, A = examples["g"], examples["illc1850"]
+    op = f77.Operator(A)
+    propack_b200.reset_counters()
+    got = f77.lansvd(op, 10, 100, tol=1e-12, u0=g["illc1850_u0"], cgs=bool(cgs))
+    ctr = propack_b200.counters()
+    oracle.stats_reset()
+    ref = oracle.lansvd(A, 10, 100, tol=1e-12, u0=g["illc1850_u0"], cgs=bool(cgs))
+    assert got["info"] == 0 and got["k"] == 10
+    assert relerr(got["sigma"], ref["sigma"]) < 1e-10                     # vs oracle
+    assert relerr(got["sigma"], g["illc1850_svd"][:10]) < 1e-10           # vs dense LAPACK
+    assert relerr(got["sigma"], g[f"illc1850_scipy_lansvd_k10_cgs{cgs}_sigma"]) < 1e-10   # vs SciPy's PROPACK
+    check_triplets(A, got, 1e-12, np.float64)
+    for i in range(10):   # singular vectors up to sign
+        assert min(np.linalg.norm(got["U"][:, i] - ref["U"][:, i]), np.linalg.norm(got["U"][:, i] + ref["U"][:, i])) < 1e-7
+        assert min(np.linalg.norm(got["V"][:, i] - ref["V"][:, i]), np.linalg.norm(got["V"][:, i] + ref["V"][:, i])) < 1e-7
+    # same Krylov trajectory as the reference algorithm: identical step and matvec counts
+    st = oracle.stats()
+    assert ctr["nsteps"] == st["nsteps"] and ctr["nopx"] == st["nopx"] and ctr["nbsvd"] == st["nbsvd"]
+    assert ctr["launches"] > 0
+    op.close()
+
+
+def test_illc1850_irl_k10(oracle, examples):
+    from propack_b200 import f77
+    g, A = examples["g"], examples["illc1850"]
+    op = f77.Operator(A)
+    got = f77.lansvd_irl(op, 10, 50, p=40, tol=1e-12, u0=g["illc1850_u0"])
+    ref = oracle.lansvd_irl(A, 10, 50, p=40, tol=1e-12, u0=g["illc1850_u0"])
+    assert got["info"] == 0 and got["k"] == 10
+    assert relerr(got["sigma"], ref["sigma"]) < 1e-10
+    assert relerr(got["sigma"], g["illc1850_svd"][:10]) < 1e-10
+    assert relerr(got["sigma"], g["illc1850_scipy_irl_k10_dim50_sigma"]) < 1e-10
+    check_triplets(A, got, 1e-12, np.float64)
+    assert subspace_dist(got["U"], ref["U"]) < 1e-6
+    op.close()
+
+
+def test_illc1850_lansvd_k200(examples):
+    """The reference's own example run (README:133-138): k=200 of 712."""
+    from propack_b200 import f77
+    g, A = examples["g"], examples["illc1850"]
+    op = f77.Operator(A)
+    got = f77.lansvd(op, 200, 712, tol=0.0, u0=g["illc1850_u0"], cgs=True)
+    assert got["info"] == 0 and got["k"] == 200
+    assert relerr(got["sigma"], g["illc1850_svd"][:200]) < 1e-10
+    assert relerr(got["sigma"], g["illc1850_scipy_lansvd_k200_sigma"]) < 1e-10
+    U, S, V = got["U"], got["sigma"], got["V"]
+    assert np.linalg.norm(U.T @ U - np.eye(200)) < 1e-6
+    assert np.linalg.norm(V.T @ V - np.eye(200)) < 1e-6
+    Ad = A.toarray()
+    u, s, vt = np.linalg.svd(Ad, full_matrices=False)
+    assert np.linalg.norm((U * S) @ V.T - (u[:, :200] * s[:200]) @ vt[:200]) < 1e-8   # SciPy test_examples check
+    op.close()
+
+
+def test_mhd1280b_zlansvd(oracle, examples):
+    """Complex example matrix of the reference (README:89-118), ZLANSVD ('c' products, zreorth)."""
+    from propack_b200 import f77
+    g, A = examples["g"], examples["mhd1280b"]
+    op = f77.Operator(A)
+    got = f77.lansvd(op, 10, 200, tol=1e-12, u0=g["mhd1280b_u0"], cgs=True)
+    ref = oracle.lansvd(A, 10, 200, tol=1e-12, u0=g["mhd1280b_u0"], cgs=True, dtype=np.complex128)
+    assert got["info"] == 0 and got["k"] == 10
+    assert relerr(got["sigma"], ref["sigma"]) < 1e-10
+    assert relerr(got["sigma"], g["mhd1280b_svd"][:10]) < 1e-10
+    assert relerr(got["sigma"], g["mhd1280b_scipy_lansvd_k10_sigma"]) < 1e-10
+    check_triplets(A, got, 1e-12, np.complex128)
+    op.close()
+
+
+def test_single_precision_examples(examples):
+    from propack_b200 import f77
+    g = examples["g"]
+    op = f77.Operator(examples["illc1850"], dtype=np.float32)
+    got = f77.lansvd(op, 10, 100, tol=1e-5, u0=g["illc1850_u0"].astype(np.float32))
+    assert got["k"] == 10 and relerr(got["sigma"], g["illc1850_svd"][:10]) < 1e-4
+    assert relerr(got["sigma"], g["illc1850_scipy_slansvd_k10_sigma"]) < 1e-4
+    op.close()
+    op = f77.Operator(examples["mhd1280b"], dtype=np.complex64)
+    got = f77.lansvd(op, 10, 200, tol=1e-5, u0=g["mhd1280b_u0"].astype(np.complex64))
+    assert got["k"] == 10 and relerr(got["sigma"], g["mhd1280b_svd"][:10]) < 1e-4
+    assert relerr(got["sigma"], g["mhd1280b_scipy_clansvd_k10_sigma"]) < 1e-4
+    op.close()
+
+
+@pytest.mark.parametrize("name", ["s", "d", "c", "z"])
+@pytest.mark.parametrize("irl", [False, True])
+@pytest.mark.parametrize("fmt", ["dense", "csr"])
+def test_scipy_test_svdp_cases(name, irl, fmt):
+    """SciPy test_propack.py::test_svdp through the scipy-compatible svdp() (k=3, 10x20)."""
+    from propack_b200 import svdp
+    t = np.load(os.path.join(GOLDEN, "small_dense.npz"))
+    A, want = t[f"A_{name}"], t[f"svd_{name}"][:3]
+    Ain = sp.csr_array(A) if fmt == "csr" else A
+    u, s, vh, _ = svdp(Ain, 3, which="LM", irl_mode=irl, kmax=11 if irl else None, full_output=True, rng=np.random.default_rng(0))
+    tol = TOL[A.dtype.type]
+    assert relerr(s, want) < tol
+    assert np.allclose(np.abs(u.conj().T @ u), np.eye(3), atol=100 * np.sqrt(np.finfo(A.dtype).eps))
+    assert np.linalg.norm(A @ vh.conj().T - u * s) < max(tol, 1e-5 if name in "sc" else 1e-9) * s[0] * 10
+
+
+def test_smallest_triplets_irl(oracle):
+    """which='S' (dlansvd_irl.F:262-275, 318-332) on a well-conditioned matrix."""
+    from propack_b200 import f77
+    rng = np.random.default_rng(4)
+    Q1, _ = np.linalg.qr(rng.standard_normal((120, 60)))
+    Q2, _ = np.linalg.qr(rng.standard_normal((60, 60)))
+    s = np.linspace(1.0, 4.0, 60)
+    A = (Q1 * s) @ Q2.T
+    op = f77.Operator(A)
+    u0 = rng.uniform(size=120)
+    got = f77.lansvd_irl(op, 3, 30, p=10, which="S", tol=1e-10, u0=u0, maxiter=300)
+    ref = oracle.lansvd_irl(A, 3, 30, p=10, which="S", tol=1e-10, u0=u0, maxiter=300)
+    assert got["k"] == ref["k"] == 3
+    assert relerr(np.sort(got["sigma"]), np.sort(s)[:3]) < 1e-8
+    assert relerr(np.sort(got["sigma"]), np.sort(ref["sigma"])) < 1e-8
+    op.close()
+
+
+def test_thin_hilbert_and_fat_random(oracle):
+    """SciPy test_thin_hilbert (200x4, k=4: j == min(m,n), dbdqr ignorelast) and test_fat_random (3x100, k=3)."""
+    from propack_b200 import f77
+    i, j = np.meshgrid(np.arange(200), np.arange(4), indexing="ij")
+    A = 1.0 / (i + j + 1)
+    op = f77.Operator(A)
+    got = f77.lansvd(op, 4, 5, u0=np.random.default_rng(0).uniform(size=200))
+    assert got["k"] == 4 and relerr(got["sigma"], np.linalg.svd(A, compute_uv=False)) < 1e-8
+    op.close()
+    B = np.random.default_rng(0).standard_normal((3, 100))
+    op = f77.Operator(B)
+    got = f77.lansvd(op, 3, 4, u0=np.random.default_rng(1).uniform(size=3))
+    assert got["k"] == 3 and relerr(got["sigma"], np.linalg.svd(B, compute_uv=False)) < 1e-10
+    op.close()
+
+
+def test_zero_start_vector_uses_lapack_rng(oracle, examples):
+    """U(:,1) = 0 => dgetu0 start vector from dlarnv(2,(1,3,5,7)) (dlansvd.F:165-169): same run as the oracle."""
+    from propack_b200 import f77
+    A = examples["illc1850"]
+    op = f77.Operator(A)
+    got = f77.lansvd(op, 6, 80, tol=1e-12, u0=None, cgs=True)
+    ref = oracle.lansvd(A, 6, 80, tol=1e-12, u0=None, cgs=True)
+    assert got["k"] == ref["k"] == 6
+    assert relerr(got["sigma"], ref["sigma"]) < 1e-10
+    op.close()
+
+
+def test_generic_callback_aprod(oracle, examples):
+    """A user APROD (LinearOperator-like, host callback with the dlansvd.F:20-33 contract) gives the same answer
+    as the device-resident operator."""
+    from propack_b200 import f77
+    from scipy.sparse.linalg import aslinearoperator
+    g, A = examples["g"], examples["illc1850"]
+    lop = aslinearoperator(A)
+    op = f77.Operator(lop)
+    got = f77.lansvd(op, 5, 60, tol=1e-12, u0=g["illc1850_u0"], cgs=True)
+    assert got["k"] == 5 and relerr(got["sigma"], g["illc1850_svd"][:5]) < 1e-10
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.complex128])
+def test_lanbpro_factorisation_and_extension(oracle, dtype):
+    """dlanbpro: A V_k = U_{k+1} B_k, then extend k0 -> k (dlanbpro.F:15-16,231-275)."""
+    from propack_b200 import f77
+    rng = np.random.default_rng(7)
+    A = rand_sparse(rng, 900, 500, 0.02, dtype)
+    op = f77.Operator(A)
+    m, n = A.shape
+    k = 30
+    U = np.zeros((m, k + 1), dtype=dtype, order="F")
+    V = np.zeros((n, k), dtype=dtype, order="F")
+    B = np.zeros((k, 2), dtype=np.float64, order="F")
+    u0 = rng.uniform(size=m).astype(dtype)
+    U[:, 0] = u0
+    k1, rnorm, ierr, anorm = f77.lanbpro(op, 0, 12, U, V, B, float(np.linalg.norm(u0)))
+    assert k1 == 12 and ierr >= 0
+    k2, rnorm, ierr, anorm = f77.lanbpro(op, 12, k, U, V, B, rnorm, anorm=anorm)
+    assert k2 == k
+    Bm = np.zeros((k + 1, k))
+    Bm[np.arange(k), np.arange(k)] = B[:, 0]
+    Bm[np.arange(1, k + 1), np.arange(k)] = B[:, 1]
+    assert np.linalg.norm(A @ V - U @ Bm) < 1e-12 * np.linalg.norm(Bm)
+    assert np.max(np.abs(U.conj().T @ U - np.eye(k + 1))) < 1e-7
+    assert np.max(np.abs(V.conj().T @ V - np.eye(k))) < 1e-7
+    assert abs(rnorm - B[k - 1, 1]) == 0
+    op.close()
+
+
+def test_complex_irl_with_restarts(oracle):
+    """Complex IRL after >= 1 restart agrees with dense SVD (the reference applies P^T/Q^T here: SURVEY 2.3)."""
+    from propack_b200 import f77
+    import propack_b200
+    rng = np.random.default_rng(3)
+    A = (rng.standard_normal((300, 200)) + 1j * rng.standard_normal((300, 200))) @ np.diag(np.linspace(1, 5, 200) ** 2)
+    op = f77.Operator(A)
+    propack_b200.reset_counters()
+    got = f77.lansvd_irl(op, 5, 12, p=6, u0=rng.uniform(size=300) + 0j, tol=1e-12)
+    assert propack_b200.counters()["nrestart"] > 0
+    assert got["k"] == 5
+    assert relerr(got["sigma"], np.linalg.svd(A, compute_uv=False)[:5]) < 1e-10
+    op.close()
+
+
+def test_medium_synthetic_matches_oracle(oracle):
+    """BASELINE config 2 recipe at 1/10 scale (100k x 100k, ~10 nnz/row, k=20): sigma vs the oracle, residuals."""
+    from propack_b200 import f77
+    rng = np.random.default_rng(0)
+    A = sp.random_array((100_000, 100_000), density=1e-4, format="csr", rng=rng, data_sampler=rng.standard_normal)
+    A.sort_indices()
+    u0 = np.random.default_rng(1).uniform(size=A.shape[0])
+    op = f77.Operator(A)
+    got = f77.lansvd(op, 20, 400, tol=1e-10, u0=u0, cgs=True)
+    ref = oracle.lansvd(A, 20, 400, tol=1e-10, u0=u0, cgs=True)
+    assert got["info"] == 0 and got["k"] == ref["k"] == 20
+    assert relerr(got["sigma"], ref["sigma"]) < 1e-10
+    check_triplets(A, got, 1e-10, np.float64)
+    assert subspace_dist(got["V"], ref["V"]) < 1e-5
+    op.close()
