@@ -70,24 +70,6 @@ bool is_yes(const char* c) { return c && (*c == 'y' || *c == 'Y'); }
 // ---------------------------------------------------------------------------------------------------
 // CSR registration: upload, device-independent host analysis of row lengths, transpose.
 // ---------------------------------------------------------------------------------------------------
-struct RowBins { int lpr; std::vector<int> med, lng; };
-RowBins analyze_rows(const int* rp, int rows) {
-  RowBins b;
-  const double mean = rows > 0 ? double(rp[rows] - rp[0]) / rows : 0.0;
-  b.lpr = mean <= 3 ? 2 : mean <= 6 ? 4 : mean <= 12 ? 8 : mean <= 24 ? 16 : 32;
-  if (const char* e = std::getenv("PROPACK_B200_SPMV_LPR")) {
-    int v = std::atoi(e);
-    if (v == 2 || v == 4 || v == 8 || v == 16 || v == 32) b.lpr = v;
-  }
-  const int short_max = 4 * b.lpr;
-  for (int i = 0; i < rows; ++i) {
-    const int len = rp[i + 1] - rp[i];
-    if (len > kCsrLongRow) b.lng.push_back(i);
-    else if (len > short_max) b.med.push_back(i);
-  }
-  return b;
-}
-
 // Stable counting-sort transpose on the host: CSR(A) -> CSR(A^T) with sorted row indices inside each
 // column -- the unique canonical form, identical to scipy's tocsc() / (A.T).tocsr() with sorted indices.
 template <class T>
@@ -107,15 +89,15 @@ void transpose_csr(int m, int n, const int* rp, const int* ci, const T* va, std:
 }
 
 template <class T> void fill_device_csr(CsrDevice<T>& D, int rows, int cols, long nnz, const DeviceBuffer<int>& rp,
-                                        const DeviceBuffer<int>& ci, const DeviceBuffer<T>& va, const RowBins& b,
-                                        DeviceBuffer<int>& bins) {
+                                        const DeviceBuffer<int>& ci, const DeviceBuffer<T>& va, const int* rp_host,
+                                        DeviceBuffer<int>& blocks) {
   D.rows = rows; D.cols = cols; D.nnz = nnz; D.rp = rp.p; D.ci = ci.p; D.va = va.p;
-  D.lanes_per_row = b.lpr;
-  D.n_med = (int)b.med.size(); D.n_long = (int)b.lng.size();
-  bins.alloc(b.med.size() + b.lng.size() + 1);
-  if (!b.med.empty()) PB_CUDA(cudaMemcpy(bins.p, b.med.data(), sizeof(int) * b.med.size(), cudaMemcpyHostToDevice));
-  if (!b.lng.empty()) PB_CUDA(cudaMemcpy(bins.p + b.med.size(), b.lng.data(), sizeof(int) * b.lng.size(), cudaMemcpyHostToDevice));
-  D.med_rows = bins.p; D.long_rows = bins.p + b.med.size();
+  const std::vector<int> blk = csr_row_blocks(rp_host, rows, spmv_block_nnz<T>());
+  blocks.alloc(blk.size());
+  PB_CUDA(cudaMemcpy(blocks.p, blk.data(), sizeof(int) * blk.size(), cudaMemcpyHostToDevice));
+  D.n_blocks = (int)blk.size() - 1;
+  D.block_row = blocks.p;
+  if (const char* e = std::getenv("PROPACK_B200_SPMV_CTAS_PER_SM")) D.ctas_per_sm = std::max(1, std::atoi(e));
 }
 
 template <class T> int csr_create(int m, int n, const int* rowptr, const int* colind, const void* values_, int base) {
@@ -150,8 +132,8 @@ template <class T> int csr_create(int m, int n, const int* rowptr, const int* co
     PB_CUDA(cudaMemcpy(op->tci.p, tci.data(), sizeof(int) * nnz, cudaMemcpyHostToDevice));
     PB_CUDA(cudaMemcpy(op->tva.p, tva.data(), sizeof(T) * nnz, cudaMemcpyHostToDevice));
   }
-  fill_device_csr<T>(op->A, m, n, nnz, op->rp, op->ci, op->va, analyze_rows(rp.data(), m), op->bins);
-  fill_device_csr<T>(op->At, n, m, nnz, op->trp, op->tci, op->tva, analyze_rows(trp.data(), n), op->tbins);
+  fill_device_csr<T>(op->A, m, n, nnz, op->rp, op->ci, op->va, rp.data(), op->bins);
+  fill_device_csr<T>(op->At, n, m, nnz, op->trp, op->tci, op->tva, trp.data(), op->tbins);
   OpEntry e; e.tag = abi<T>::tag; e.kind = 0; e.op = op;
   const int h = g_next_op++;
   g_ops[h] = e;

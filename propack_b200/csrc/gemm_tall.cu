@@ -5,18 +5,19 @@
 // variant zdgemm_ovwr_left (complex16/zgemm_ovwr.F:6-61) multiplies a complex basis by a REAL
 // small matrix, which is the same real GEMM on the interleaved (re,im) rows (2M rows, ld 2*lda).
 // The reference streams row blocks through a scratch buffer because BLAS dgemm cannot work in
-// place.  Here a warp owns 8 rows for the whole K sweep and holds its 8 x N result in DMMA
+// place.  Here a warp owns 8*MT rows for the whole K sweep and holds its (8*MT) x N result in DMMA
 // accumulator registers, so the product is written back over the same rows once every column of
 // those rows has been read: in place, no scratch, M*(K+N)*w bytes of HBM traffic.
 //
 //   - mma.sync.aligned.m8n8k4.row.col.f64 (SASS: DMMA.8x8x4); tcgen05 has no FP64 kind.
 //   - A fragments: one LDG.64 per lane per k-step straight from HBM (8 consecutive rows x 4
-//     columns = four 64-byte segments, every 32-byte sector fully used); no reuse across warps
-//     exists for the tall operand, so shared-memory staging would add nothing.
-//   - W is pre-packed on the host in fragment order (pack_w below), so a B fragment is one
-//     coalesced 256-byte warp load served by L1/L2 (W is K*N*8 <= ~0.6 MB, shared by every warp).
-//   - N > 128 (more accumulators than registers): column slabs of 128 go through a per-warp
-//     L2-resident scratch strip and are copied over A after the last slab.
+//     columns = four 64-byte segments, every 32-byte sector fully used), prefetched one K chunk
+//     ahead; the tall operand has no reuse across warps, so it is not staged in shared memory.
+//   - W is pre-packed on the host in DMMA B-fragment order (pack_w below); the CTA stages one
+//     K chunk of it in shared memory (conflict-free 256-byte rows) and all 8 warps x MT m-tiles
+//     reuse it, so W traffic from L2 is |W| per 64*MT rows instead of per 8 rows.
+//   - N > 128 (more accumulators than registers): column slabs of 128 go through a scratch panel
+//     and are copied over A after the last slab.
 //   - float / complex-float bases are widened to FP64 on load (same kernel, half the bytes).
 // Arithmetic intensity 2KN/(w(K+N)) ~ N/4 flop/B: FP64-pipe bound for N >~ 25.
 #include <algorithm>
@@ -34,44 +35,80 @@ __device__ inline void dmma(double& c0, double& c1, double a, double b) {
                : "d"(a), "d"(b));
 }
 
-// NT = n-tiles (of 8 columns) held in registers by one warp.
-template <class R, int NT>
+// NT = n-tiles (8 columns each) and MT = m-tiles (8 rows each) held in DMMA accumulators by one warp.
+// The CTA (8 warps) owns 64*MT consecutive rows; all warps walk K in lock step, KS k-steps (4 columns
+// each) at a time, sharing one shared-memory copy of the packed W chunk; A fragments for the next
+// chunk are prefetched from HBM into registers while the current chunk is multiplied.
+constexpr int GK_KS = 4;
+template <class R, int NT, int MT>
 __global__ void __launch_bounds__(kThreads)
 gemm_tall_kernel(long Mr, int N, int K, R* A, long lda, const double* __restrict__ Wp, int nt_total, int nt0,
                  R* dst, long ldd) {
-  const int lane = threadIdx.x & 31;
+  __shared__ __align__(16) double wsm[GK_KS * NT * 32];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int kk = lane & 3, rr = lane >> 2;
-  const long nwarps = (long)gridDim.x * (kThreads / 32);
   const int ksteps = (K + 3) / 4;
-  for (long blk = (long)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5); blk * 8 < Mr; blk += nwarps) {
-    const long row = blk * 8 + rr;
-    const bool rok = row < Mr;
-    double c[NT][2];
+  const int nchunks = (ksteps + GK_KS - 1) / GK_KS;
+  const long tile_rows = 64L * MT;
+  for (long t0 = (long)blockIdx.x * tile_rows; t0 < Mr; t0 += (long)gridDim.x * tile_rows) {
+    long row[MT];
+    bool rok[MT];
 #pragma unroll
-    for (int j = 0; j < NT; ++j) { c[j][0] = 0.0; c[j][1] = 0.0; }
-    const R* ap = A + row + (long)kk * lda;
-    const double* wp = Wp + (long)nt0 * 32 + lane;
-#pragma unroll 4
-    for (int s = 0; s < ksteps; ++s) {
-      const int k = 4 * s + kk;
-      double a = 0.0;
-      if (rok && k < K) a = (double)ap[(long)(4 * s) * lda];
+    for (int mt = 0; mt < MT; ++mt) { row[mt] = t0 + (long)(wid * MT + mt) * 8 + rr; rok[mt] = row[mt] < Mr; }
+    double c[MT][NT][2];
 #pragma unroll
-      for (int j = 0; j < NT; ++j) {
-        const double b = __ldg(wp + ((long)s * nt_total + j) * 32);
-        dmma(c[j][0], c[j][1], a, b);
+    for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+      for (int j = 0; j < NT; ++j) { c[mt][j][0] = 0.0; c[mt][j][1] = 0.0; }
+    double a_cur[GK_KS][MT], a_nxt[GK_KS][MT];
+    auto load_a = [&](int chunk, double (&a)[GK_KS][MT]) {
+#pragma unroll
+      for (int s = 0; s < GK_KS; ++s) {
+        const int k = 4 * (chunk * GK_KS + s) + kk;
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt) a[s][mt] = (rok[mt] && k < K) ? (double)A[(long)k * lda + row[mt]] : 0.0;
       }
-    }
-    // all K columns of these 8 rows have been read by this warp: safe to overwrite in place
-    if (rok) {
-#pragma unroll
-      for (int j = 0; j < NT; ++j)
-#pragma unroll
-        for (int i = 0; i < 2; ++i) {
-          const int col = (nt0 + j) * 8 + 2 * kk + i;
-          if (col < N) dst[(long)col * ldd + row] = (R)c[j][i];
+    };
+    load_a(0, a_cur);
+    for (int ch = 0; ch < nchunks; ++ch) {
+      __syncthreads();  // previous chunk's W fully consumed
+      {
+        const int s_lo = ch * GK_KS;
+        for (int i = threadIdx.x; i < GK_KS * NT * 32; i += kThreads) {
+          const int s = i / (NT * 32), rem = i - s * (NT * 32);
+          const int j = rem >> 5, l = rem & 31;
+          double v = 0.0;
+          if (s_lo + s < ksteps) v = __ldg(Wp + ((long)(s_lo + s) * nt_total + nt0 + j) * 32 + l);
+          wsm[i] = v;
         }
+      }
+      if (ch + 1 < nchunks) load_a(ch + 1, a_nxt);
+      __syncthreads();
+#pragma unroll
+      for (int s = 0; s < GK_KS; ++s)
+#pragma unroll
+        for (int j = 0; j < NT; ++j) {
+          const double b = wsm[(s * NT + j) * 32 + lane];
+#pragma unroll
+          for (int mt = 0; mt < MT; ++mt) dmma(c[mt][j][0], c[mt][j][1], a_cur[s][mt], b);
+        }
+#pragma unroll
+      for (int s = 0; s < GK_KS; ++s)
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt) a_cur[s][mt] = a_nxt[s][mt];
     }
+    // every column of this warp's rows has been read (the last mma.sync joins the warp): overwrite in place
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt)
+      if (rok[mt]) {
+#pragma unroll
+        for (int j = 0; j < NT; ++j)
+#pragma unroll
+          for (int i = 0; i < 2; ++i) {
+            const int col = (nt0 + j) * 8 + 2 * kk + i;
+            if (col < N) dst[(long)col * ldd + row[mt]] = (R)c[mt][j][i];
+          }
+      }
   }
 }
 
@@ -83,22 +120,22 @@ copy_cols_kernel(long Mr, int N, const R* __restrict__ src, long lds, R* __restr
       dst[(long)col * ldd + r] = src[(long)col * lds + r];
 }
 
-template <class R, int NT>
+template <class R, int NT, int MT>
 void launch_slab(Context& c, long Mr, int N, int K, R* A, long lda, const double* Wp, int nt_total, int nt0, R* dst, long ldd) {
-  const int grid = c.grid_for((Mr + 7) / 8, kThreads / 32, 4);
-  gemm_tall_kernel<R, NT><<<grid, kThreads, 0, c.stream>>>(Mr, N, K, A, lda, Wp, nt_total, nt0, dst, ldd);
+  const int grid = c.grid_for(Mr, 64 * MT, 2);
+  gemm_tall_kernel<R, NT, MT><<<grid, kThreads, 0, c.stream>>>(Mr, N, K, A, lda, Wp, nt_total, nt0, dst, ldd);
   PB_LAUNCH_CHECK();
   c.ctr.launches += 1;
 }
 
 template <class R>
 void slab(Context& c, int nt, long Mr, int N, int K, R* A, long lda, const double* Wp, int nt_total, int nt0, R* dst, long ldd) {
-  if (nt <= 2) launch_slab<R, 2>(c, Mr, N, K, A, lda, Wp, nt_total, nt0, dst, ldd);
-  else if (nt <= 4) launch_slab<R, 4>(c, Mr, N, K, A, lda, Wp, nt_total, nt0, dst, ldd);
-  else if (nt <= 7) launch_slab<R, 7>(c, Mr, N, K, A, lda, Wp, nt_total, nt0, dst, ldd);
-  else if (nt <= 10) launch_slab<R, 10>(c, Mr, N, K, A, lda, Wp, nt_total, nt0, dst, ldd);
-  else if (nt <= 13) launch_slab<R, 13>(c, Mr, N, K, A, lda, Wp, nt_total, nt0, dst, ldd);
-  else launch_slab<R, 16>(c, Mr, N, K, A, lda, Wp, nt_total, nt0, dst, ldd);
+  if (nt <= 2) launch_slab<R, 2, 4>(c, Mr, N, K, A, lda, Wp, nt_total, nt0, dst, ldd);
+  else if (nt <= 4) launch_slab<R, 4, 4>(c, Mr, N, K, A, lda, Wp, nt_total, nt0, dst, ldd);
+  else if (nt <= 7) launch_slab<R, 7, 2>(c, Mr, N, K, A, lda, Wp, nt_total, nt0, dst, ldd);
+  else if (nt <= 10) launch_slab<R, 10, 1>(c, Mr, N, K, A, lda, Wp, nt_total, nt0, dst, ldd);
+  else if (nt <= 13) launch_slab<R, 13, 1>(c, Mr, N, K, A, lda, Wp, nt_total, nt0, dst, ldd);
+  else launch_slab<R, 16, 1>(c, Mr, N, K, A, lda, Wp, nt_total, nt0, dst, ldd);
 }
 
 // real GEMM on Mr real rows

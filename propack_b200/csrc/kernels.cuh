@@ -2,6 +2,8 @@
 // Each wrapper enqueues on Context::stream and never synchronises; results the host must branch
 // on come back through Context::Pending slots (see common.cuh).
 #pragma once
+#include <vector>
+
 #include "common.cuh"
 #include "context.hpp"
 
@@ -33,21 +35,21 @@ void k_gemv_n(Context& c, long L, int l, const T* V, long ldv, const T* h, real_
               Pending* nrm);
 
 // --- CSR SpMV (reference: the user's APROD, dlansvd.F:20-33; call sites dlanbpro.F:288,420) --------
+constexpr int kSpmvRows = 256;  // max rows per SpMV row block (one CTA pass)
+// non-zeros per row block = a 32 KB shared-memory product buffer
+template <class T> constexpr int spmv_block_nnz() { return 32768 / (int)sizeof(T); }
 template <class T> struct CsrDevice {
   int rows = 0, cols = 0;
   long nnz = 0;
   const int* rp = nullptr;     // [rows+1]
   const int* ci = nullptr;     // [nnz], sorted within a row
   const T* va = nullptr;       // [nnz]
-  int lanes_per_row = 8;       // LPR: sub-warp width chosen from the mean row length
-  // row bins (csr_analyze): short rows (<= 4*LPR nnz) are found by scanning all rows;
-  // medium (<= kCsrLongRow nnz) and long rows are listed explicitly.
-  int n_med = 0;
-  const int* med_rows = nullptr;
-  int n_long = 0;
-  const int* long_rows = nullptr;
+  int n_blocks = 0;            // row blocks (csr_row_blocks): block b covers rows block_row[b] .. block_row[b+1]
+  const int* block_row = nullptr;
+  int ctas_per_sm = 6;
 };
-constexpr int kCsrLongRow = 2048;
+// host-side analysis: cut rows into blocks of <= kSpmvRows rows and <= nb non-zeros (longer rows stand alone)
+std::vector<int> csr_row_blocks(const int* rp, int rows, int nb);
 // y <- op(A) x + coef*prev (prev may be null) ; optionally publish ||y||_2.  conj: use conj(values).
 template <class T>
 void k_spmv(Context& c, const CsrDevice<T>& A, bool conj, const T* x, T* y, real_t<T> coef, const T* prev, Pending* nrm);

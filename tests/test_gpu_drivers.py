@@ -71,7 +71,7 @@ def test_illc1850_irl_k10(oracle, examples):
     assert relerr(got["sigma"], g["illc1850_svd"][:10]) < 1e-10
     assert relerr(got["sigma"], g["illc1850_scipy_irl_k10_dim50_sigma"]) < 1e-10
     check_triplets(A, got, 1e-12, np.float64)
-    assert subspace_dist(got["U"], ref["U"]) < 1e-6
+    assert subspace_dist(got["U"], ref["U"]) < 1e-5   # Ritz vectors of a semiorthogonal (sqrt(eps)) basis
     op.close()
 
 
