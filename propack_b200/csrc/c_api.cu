@@ -89,15 +89,10 @@ void transpose_csr(int m, int n, const int* rp, const int* ci, const T* va, std:
 }
 
 template <class T> void fill_device_csr(CsrDevice<T>& D, int rows, int cols, long nnz, const DeviceBuffer<int>& rp,
-                                        const DeviceBuffer<int>& ci, const DeviceBuffer<T>& va, const int* rp_host,
-                                        DeviceBuffer<int>& blocks) {
+                                        const DeviceBuffer<int>& ci, const DeviceBuffer<T>& va) {
   D.rows = rows; D.cols = cols; D.nnz = nnz; D.rp = rp.p; D.ci = ci.p; D.va = va.p;
-  const std::vector<int> blk = csr_row_blocks(rp_host, rows, spmv_block_nnz<T>());
-  blocks.alloc(blk.size());
-  PB_CUDA(cudaMemcpy(blocks.p, blk.data(), sizeof(int) * blk.size(), cudaMemcpyHostToDevice));
-  D.n_blocks = (int)blk.size() - 1;
-  D.block_row = blocks.p;
-  if (const char* e = std::getenv("PROPACK_B200_SPMV_CTAS_PER_SM")) D.ctas_per_sm = std::max(1, std::atoi(e));
+  D.lpr_log2 = csr_lanes_per_row_log2(nnz, rows, spmv_group_nnz<T>());
+  if (const char* e = std::getenv("PROPACK_B200_SPMV_LPR_LOG2")) D.lpr_log2 = std::min(5, std::max(0, std::atoi(e)));
 }
 
 template <class T> int csr_create(int m, int n, const int* rowptr, const int* colind, const void* values_, int base) {
@@ -132,8 +127,8 @@ template <class T> int csr_create(int m, int n, const int* rowptr, const int* co
     PB_CUDA(cudaMemcpy(op->tci.p, tci.data(), sizeof(int) * nnz, cudaMemcpyHostToDevice));
     PB_CUDA(cudaMemcpy(op->tva.p, tva.data(), sizeof(T) * nnz, cudaMemcpyHostToDevice));
   }
-  fill_device_csr<T>(op->A, m, n, nnz, op->rp, op->ci, op->va, rp.data(), op->bins);
-  fill_device_csr<T>(op->At, n, m, nnz, op->trp, op->tci, op->tva, trp.data(), op->tbins);
+  fill_device_csr<T>(op->A, m, n, nnz, op->rp, op->ci, op->va);
+  fill_device_csr<T>(op->At, n, m, nnz, op->trp, op->tci, op->tva);
   OpEntry e; e.tag = abi<T>::tag; e.kind = 0; e.op = op;
   const int h = g_next_op++;
   g_ops[h] = e;

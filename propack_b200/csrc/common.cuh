@@ -120,6 +120,9 @@ __device__ inline double shfl_down_(double v, int d, int w = 32) { return __shfl
 template <class R> __device__ inline cplx<R> shfl_down_(cplx<R> v, int d, int w = 32) {
   return cplx<R>(shfl_down_(v.x, d, w), shfl_down_(v.y, d, w));
 }
+__device__ inline float shfl_idx_(float v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+__device__ inline double shfl_idx_(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+template <class R> __device__ inline cplx<R> shfl_idx_(cplx<R> v, int src) { return cplx<R>(shfl_idx_(v.x, src), shfl_idx_(v.y, src)); }
 template <class T> __device__ inline T warp_sum(T v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v = v + shfl_xor_(v, o);

@@ -44,7 +44,7 @@ template <class T> struct LinOp {
 
 template <class T> struct CsrOperator : LinOp<T> {
   using R = real_t<T>;
-  DeviceBuffer<int> rp, ci, trp, tci, bins, tbins;
+  DeviceBuffer<int> rp, ci, trp, tci;
   DeviceBuffer<T> va, tva;
   CsrDevice<T> A, At;  // At = CSR of A^T (values not conjugated)
   void apply(Context& c, bool adjoint, const T* x, T* y, R coef, const T* prev, Pending* nrm) override {

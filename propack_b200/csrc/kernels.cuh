@@ -35,21 +35,21 @@ void k_gemv_n(Context& c, long L, int l, const T* V, long ldv, const T* h, real_
               Pending* nrm);
 
 // --- CSR SpMV (reference: the user's APROD, dlansvd.F:20-33; call sites dlanbpro.F:288,420) --------
-constexpr int kSpmvRows = 256;  // max rows per SpMV row block (one CTA pass)
-// non-zeros per row block = a 32 KB shared-memory product buffer
-template <class T> constexpr int spmv_block_nnz() { return 32768 / (int)sizeof(T); }
+constexpr int kSpmvU = 4;            // independent (ci -> x) gather chains per lane per batch
+constexpr int kSpmvCtasPerSm = 3;    // persistent CTAs per SM (3 x 32 KB of shared memory: L1 keeps ~130 KB)
+constexpr int kSpmvCarveoutPct = 50; // cudaFuncAttributePreferredSharedMemoryCarveout: the 132 KB configuration (3 CTAs x ~34 KB need > 100 KB)
+// non-zeros per row group = a 4 KB shared-memory slice per warp
+template <class T> constexpr int spmv_group_nnz() { return 4096 / (int)sizeof(T); }
 template <class T> struct CsrDevice {
   int rows = 0, cols = 0;
   long nnz = 0;
   const int* rp = nullptr;     // [rows+1]
   const int* ci = nullptr;     // [nnz], sorted within a row
   const T* va = nullptr;       // [nnz]
-  int n_blocks = 0;            // row blocks (csr_row_blocks): block b covers rows block_row[b] .. block_row[b+1]
-  const int* block_row = nullptr;
-  int ctas_per_sm = 6;
+  int lpr_log2 = 0;            // lanes per row in the reduce phase = 1 << lpr_log2 (csr_lanes_per_row_log2)
 };
-// host-side analysis: cut rows into blocks of <= kSpmvRows rows and <= nb non-zeros (longer rows stand alone)
-std::vector<int> csr_row_blocks(const int* rp, int rows, int nb);
+// host-side analysis: lanes per row so that a group of 32/LPR rows fits a slice of nb products
+int csr_lanes_per_row_log2(long nnz, int rows, int nb);
 // y <- op(A) x + coef*prev (prev may be null) ; optionally publish ||y||_2.  conj: use conj(values).
 template <class T>
 void k_spmv(Context& c, const CsrDevice<T>& A, bool conj, const T* x, T* y, real_t<T> coef, const T* prev, Pending* nrm);

@@ -8,20 +8,21 @@
 // A^T (= CSC of A), so both directions are the same gather-style kernel: no atomics, no
 // transpose-time scatter, bit-reproducible.
 //
-// Kernel organisation ("row blocks", computed once per matrix by csr_row_blocks()):
-//   rows are cut into consecutive blocks of <= kSpmvRows rows and <= NB non-zeros (NB = what fits
-//   the CTA's shared-memory product buffer); a row longer than NB is a block of its own.
-//   phase 1  the CTA streams the block's (ci, va) slice with fully coalesced, 4-way unrolled loads,
-//            gathers x through the read-only path and parks the products in shared memory --
-//            every lane has 4 independent (ci -> x) chains in flight regardless of row lengths;
-//   phase 2  rows are reduced out of shared memory by sub-warps whose width follows the block's
-//            mean row length (4 lanes for ~10 nnz/row, a warp for power-law rows), then the
-//            epilogue  y = sum + coef*prev  and the ||y||^2 partial.
-//   long rows (> NB nnz) are swept by the whole CTA.
-// (ci, va) are touched once per launch: evict-first loads keep them from displacing x in L2
-// (x is 8 MB at 1M columns, 80 MB at 10M; L2 is 126 MB).
-// HBM-bound: algorithmic bytes nnz*(w+4) + 4(rows+1) + w*cols + w*rows (+ w*rows for prev); the
-// x gathers (one 32-byte sector per non-zero for random columns) ride on L2 bandwidth.
+// Organisation ("warp-private row groups"; chosen from the measurements in profiles/r01_spmv_lab.md):
+//   * a row group = RPG = 32/LPR consecutive rows, LPR (a power of two, lanes per row) picked per matrix from
+//     the mean row length so that a group's non-zeros fit the warp's 4 KB shared-memory slice;
+//   * phase 1: the warp streams the group's (ci, va) slice with coalesced loads in batches of kSpmvU
+//     independent (ci -> x) gather chains per lane and parks the products in its slice;
+//   * phase 2: LPR lanes reduce each row out of shared memory, then y = sum + coef*prev and the ||y||^2 partial;
+//   * no CTA-wide barrier anywhere in the loop: every warp runs its own load/gather/reduce pipeline, and the
+//     next group's row pointers are fetched while the current gathers are in flight;
+//   * a group holding a row too long for the slice falls back to warp-per-row sweeps from global memory.
+// The random x gathers make this kernel L1TEX-wavefront bound, not HBM bound (one wavefront per gathered lane:
+// 10 M gathers take >= 44 us on a B200 however the rest is organised).  L1 also tracks the outstanding misses,
+// so the shared-memory footprint is capped (3 CTAs x 33 KB per SM, carve-out hint 50% = the 132 KB configuration): with the carve-out at
+// the maximum the same gathers run 3x slower.
+// HBM traffic: nnz*(w+4) + 4(rows+1) + w*cols + w*rows (+ w*rows for prev); (ci, va) are touched once per
+// launch and loaded evict-first so they do not displace x in L2 (x is 8 MB at 1M columns, 80 MB at 10M).
 #include <algorithm>
 
 #include "kernels.cuh"
@@ -60,89 +61,90 @@ template <class T, bool CONJ> __device__ inline T mul_(T a, T x) {
   return acc;
 }
 
+constexpr int kSpmvWarps = kThreads / 32;
+
 template <class T, bool CONJ>
 __global__ void __launch_bounds__(kThreads)
 spmv_kernel(CsrDevice<T> A, const T* __restrict__ x, T* __restrict__ y, real_t<T> coef, const T* __restrict__ prev,
             ReduceWs ws, int want_norm) {
-  constexpr int NB = spmv_block_nnz<T>();
-  __shared__ T prod[NB];
-  __shared__ int srp[kSpmvRows + 1];
+  constexpr int NB = spmv_group_nnz<T>();
+  __shared__ T prod[kSpmvWarps][NB];
   __shared__ double red[32];
-  __shared__ T redT[32];
-  const int tid = threadIdx.x;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int lpr_log2 = A.lpr_log2, lpr = 1 << lpr_log2, rpg = 32 >> lpr_log2;
+  const int sub = lane >> lpr_log2, lg = lane & (lpr - 1);
+  T* pw = prod[w];
   double nrm = 0.0;
-
-  for (int b = blockIdx.x; b < A.n_blocks; b += gridDim.x) {
-    const int r0 = __ldg(A.block_row + b), r1 = __ldg(A.block_row + b + 1);
-    const int nrows = r1 - r0;
-    for (int i = tid; i <= nrows; i += kThreads) srp[i] = __ldg(A.rp + r0 + i);
-    __syncthreads();
-    const int p0 = srp[0];
-    const int nnzb = srp[nrows] - p0;
-
-    if (nnzb > NB) {
-      // ---- a single long row: CTA-wide strided sweep -------------------------------------------
-      T acc = zero_<T>();
-      for (int p = p0 + tid; p < p0 + nnzb; p += kThreads) {
-        const T a = ldcs_(A.va + p);
-        const T xv = ldg_(x + __ldcs(A.ci + p));
-        if (CONJ) fma_conj(acc, a, xv);
-        else fma_(acc, a, xv);
-      }
-      acc = block_sum(acc, redT);
-      if (tid == 0) {
-        if (prev != nullptr) acc = acc + coef * prev[r0];
-        y[r0] = acc;
-        nrm += (double)abs2_(acc);
-      }
-      __syncthreads();
-      continue;
-    }
-
-    // ---- phase 1: products into shared memory ------------------------------------------------------
-    {
+  const long ngroups = ((long)A.rows + rpg - 1) / rpg;
+  const long gstride = (long)gridDim.x * kSpmvWarps;
+  long g = (long)blockIdx.x * kSpmvWarps + w;
+  // lane (sub, lg) carries the extent [s, e) of row g*rpg + sub; lanes past the last row carry an empty extent
+  auto load_extent = [&](long gg, int& s, int& e) {
+    const long row = gg * rpg + sub;
+    const bool ok = gg < ngroups && row < A.rows;
+    s = __ldg(A.rp + (ok ? row : (long)A.rows));
+    e = __ldg(A.rp + (ok ? row + 1 : (long)A.rows));
+  };
+  int s, e;
+  load_extent(g, s, e);
+  for (; g < ngroups; g += gstride) {
+    int sn, en;
+    load_extent(g + gstride, sn, en);  // prefetch the next group's extents
+    const long row = g * rpg + sub;
+    const bool ok = row < A.rows;
+    const int p0 = __shfl_sync(0xffffffffu, s, 0), pe = __shfl_sync(0xffffffffu, e, 31);
+    const int nn = pe - p0;
+    T pv = zero_<T>();
+    if (ok && prev != nullptr && lg == 0) pv = ldcs_(prev + row);
+    if (nn <= NB) {
+      // ---- phase 1: products of the group's slice into the warp's shared-memory slice -----------------
       const int* cip = A.ci + p0;
       const T* vap = A.va + p0;
-      int i = tid;
-      for (; i + 3 * kThreads < nnzb; i += 4 * kThreads) {
-        const int c0 = __ldcs(cip + i), c1 = __ldcs(cip + i + kThreads), c2 = __ldcs(cip + i + 2 * kThreads),
-                  c3 = __ldcs(cip + i + 3 * kThreads);
-        const T a0 = ldcs_(vap + i), a1 = ldcs_(vap + i + kThreads), a2 = ldcs_(vap + i + 2 * kThreads),
-                a3 = ldcs_(vap + i + 3 * kThreads);
-        const T x0 = ldg_(x + c0), x1 = ldg_(x + c1), x2 = ldg_(x + c2), x3 = ldg_(x + c3);
-        prod[i] = mul_<T, CONJ>(a0, x0);
-        prod[i + kThreads] = mul_<T, CONJ>(a1, x1);
-        prod[i + 2 * kThreads] = mul_<T, CONJ>(a2, x2);
-        prod[i + 3 * kThreads] = mul_<T, CONJ>(a3, x3);
+      for (int i0 = 0; i0 < nn; i0 += kSpmvU * 32) {
+        int c[kSpmvU];
+        T a[kSpmvU], xv[kSpmvU];
+#pragma unroll
+        for (int u = 0; u < kSpmvU; ++u) { const int i = i0 + u * 32 + lane; c[u] = i < nn ? __ldcs(cip + i) : -1; }
+#pragma unroll
+        for (int u = 0; u < kSpmvU; ++u) { const int i = i0 + u * 32 + lane; a[u] = i < nn ? ldcs_(vap + i) : zero_<T>(); }
+#pragma unroll
+        for (int u = 0; u < kSpmvU; ++u) xv[u] = c[u] >= 0 ? ldg_(x + c[u]) : zero_<T>();
+#pragma unroll
+        for (int u = 0; u < kSpmvU; ++u) { const int i = i0 + u * 32 + lane; if (i < nn) pw[i] = mul_<T, CONJ>(a[u], xv[u]); }
       }
-      for (; i < nnzb; i += kThreads) prod[i] = mul_<T, CONJ>(ldcs_(vap + i), ldg_(x + __ldcs(cip + i)));
-    }
-    __syncthreads();
-
-    // ---- phase 2: per-row reduction by sub-warps of `lpr` lanes ----------------------------------------
-    {
-      const int mean = (nnzb + nrows - 1) / max(nrows, 1);
-      int lpr = 4;
-      while (lpr < 32 && lpr * 4 < mean) lpr <<= 1;
-      const int gpc = kThreads / lpr;             // rows per pass
-      const int g = tid / lpr, lg = tid % lpr;
-      for (int rbase = 0; rbase < nrows; rbase += gpc) {   // CTA-uniform trip count
-        const int r = rbase + g;
+      __syncwarp();
+      // ---- phase 2: LPR lanes per row ----------------------------------------------------------------------
+      T acc = zero_<T>();
+      for (int q = s - p0 + lg; q < e - p0; q += lpr) acc = acc + pw[q];
+      for (int o = lpr >> 1; o > 0; o >>= 1) acc = acc + shfl_down_(acc, o, lpr);
+      __syncwarp();  // the slice is rewritten by the next group
+      if (ok && lg == 0) {
+        if (prev != nullptr) acc = acc + coef * pv;
+        y[row] = acc;
+        nrm += (double)abs2_(acc);
+      }
+    } else {
+      // ---- a row too long for the slice is in this group: warp-per-row sweeps from global memory --------
+      for (int r = 0; r < rpg; ++r) {
+        const int rs = __shfl_sync(0xffffffffu, s, r << lpr_log2), re = __shfl_sync(0xffffffffu, e, r << lpr_log2);
         T acc = zero_<T>();
-        if (r < nrows) {
-          const int s = srp[r] - p0, e = srp[r + 1] - p0;
-          for (int q = s + lg; q < e; q += lpr) acc = acc + prod[q];
+        for (int p = rs + lane; p < re; p += 32) {
+          const T a = ldcs_(A.va + p);
+          const T xv = ldg_(x + __ldcs(A.ci + p));
+          if (CONJ) fma_conj(acc, a, xv);
+          else fma_(acc, a, xv);
         }
-        for (int o = lpr >> 1; o > 0; o >>= 1) acc = acc + shfl_down_(acc, o, lpr);
-        if (lg == 0 && r < nrows) {
-          const long row = (long)r0 + r;
-          if (prev != nullptr) acc = acc + coef * prev[row];
-          y[row] = acc;
+        acc = warp_sum(acc);
+        const T pr = shfl_idx_(pv, r << lpr_log2);
+        const long rr = g * rpg + r;
+        if (lane == 0 && rr < A.rows) {
+          if (prev != nullptr) acc = acc + coef * pr;
+          y[rr] = acc;
           nrm += (double)abs2_(acc);
         }
       }
     }
-    __syncthreads();  // prod / srp are reused by the next block
+    s = sn; e = en;
   }
   if (want_norm) {
     double tot = block_sum(nrm, red);
@@ -157,7 +159,15 @@ void k_spmv(Context& c, const CsrDevice<T>& A, bool conj, const T* x, T* y, real
   ReduceWs ws{};
   int want = 0;
   if (nrm) { ws = c.new_reduce(nrm); want = 1; }
-  const int grid = c.grid_for(A.n_blocks, 1, A.ctas_per_sm);
+  const int rpg = 32 >> A.lpr_log2;
+  const long ngroups = ((long)A.rows + rpg - 1) / rpg;
+  const int grid = c.grid_for(ngroups, kSpmvWarps, kSpmvCtasPerSm);
+  static bool attr_set = false;
+  if (!attr_set) {  // keep most of the 228 KB for L1: it tracks the outstanding gather misses
+    PB_CUDA(cudaFuncSetAttribute(spmv_kernel<T, true>, cudaFuncAttributePreferredSharedMemoryCarveout, kSpmvCarveoutPct));
+    PB_CUDA(cudaFuncSetAttribute(spmv_kernel<T, false>, cudaFuncAttributePreferredSharedMemoryCarveout, kSpmvCarveoutPct));
+    attr_set = true;
+  }
   if (conj && scalar_traits<T>::is_complex)
     spmv_kernel<T, true><<<grid, kThreads, 0, c.stream>>>(A, x, y, coef, prev, ws, want);
   else
@@ -166,25 +176,15 @@ void k_spmv(Context& c, const CsrDevice<T>& A, bool conj, const T* x, T* y, real
   c.ctr.launches += 1;
 }
 
-// Cut rows into blocks of <= kSpmvRows rows and <= nb non-zeros; longer rows stand alone.
-std::vector<int> csr_row_blocks(const int* rp, int rows, int nb) {
-  std::vector<int> blk;
-  blk.push_back(0);
-  int start = 0;
-  while (start < rows) {
-    int end = start;
-    long nnz = 0;
-    while (end < rows && end - start < kSpmvRows) {
-      const long len = rp[end + 1] - rp[end];
-      if (nnz + len > nb) break;
-      nnz += len;
-      ++end;
-    }
-    if (end == start) ++end;  // a single row longer than nb
-    blk.push_back(end);
-    start = end;
-  }
-  return blk;
+// Lanes per row for a matrix with `nnz` non-zeros in `rows` rows: the largest row group (32/LPR rows) whose
+// expected non-zero count, with 30% head-room for row-length spread, fits the warp's slice of `nb` entries.
+int csr_lanes_per_row_log2(long nnz, int rows, int nb) {
+  const double mean = rows > 0 ? (double)nnz / rows : 0.0;
+  int rpg = 32;
+  while (rpg > 1 && rpg * 1.3 * mean > nb) rpg >>= 1;
+  int l = 0;
+  while ((32 >> l) > rpg) ++l;
+  return l;
 }
 
 #define PB_INST(T) \
