@@ -221,6 +221,33 @@ int propack_b200_solver_get_u(int solver, int ncols, void* U_host, long ldu);
 int propack_b200_solver_get_v(int solver, int ncols, void* V_host, long ldv);
 
 /* ---- runtime --------------------------------------------------------------------------------------- */
+/* ---- multi-GPU: one process per GPU.  The reference has no distributed layer; its only
+ * parallelism is OpenMP row-chunking of the same loops (double/dreorth.F:147-208, double/dritzvec.F:145-196), which
+ * is the scheme these entry points lift across GPUs.  Rank 0 calls _comm_unique_id, the caller broadcasts the 128
+ * bytes (MPI, torch.distributed, a file ...), every rank calls _comm_init (collective). ---- */
+int propack_b200_comm_unique_id(void* id128_out);
+int propack_b200_comm_init(int rank, int world, const void* id128);
+int propack_b200_comm_finalize(void);
+int propack_b200_comm_rank(void);
+int propack_b200_comm_world(void);
+/* block partition used for rows of A / U (dim = m) and for V-vectors (dim = n): rank r owns [lo, hi) */
+long propack_b200_shard_slice(long dim, int world);
+void propack_b200_shard_bounds(long dim, int world, int rank, long* lo, long* hi);
+void propack_b200_comm_stats(long long* n_allreduce, long long* n_allgather, double* allgather_bytes);
+/* Row-sharded operator of THIS rank: row_* = CSR of A[r0:r1, :] (global column ids); colt_* = CSR of (A[:, c0:c1])^T
+ * (global row ids); [r0,r1) and [c0,c1) from _shard_bounds for this rank.  Replaces the user's APROD (contract
+ * double/dlansvd.F:20-33) by: all-gather the input vector, then a local SpMV (both directions). */
+int propack_b200_csr_create_sharded_s(int m_global, int n_global, const int* row_rowptr, const int* row_colind, const float* row_values,
+                                      const int* colt_rowptr, const int* colt_rowind, const float* colt_values, int index_base);
+int propack_b200_csr_create_sharded_d(int m_global, int n_global, const int* row_rowptr, const int* row_colind, const double* row_values,
+                                      const int* colt_rowptr, const int* colt_rowind, const double* colt_values, int index_base);
+int propack_b200_csr_create_sharded_c(int m_global, int n_global, const int* row_rowptr, const int* row_colind, const pb200_complex8* row_values,
+                                      const int* colt_rowptr, const int* colt_rowind, const pb200_complex8* colt_values, int index_base);
+int propack_b200_csr_create_sharded_z(int m_global, int n_global, const int* row_rowptr, const int* row_colind, const pb200_complex16* row_values,
+                                      const int* colt_rowptr, const int* colt_rowind, const pb200_complex16* colt_values, int index_base);
+/* local slice sizes of a solver session (U is m_local x ucols with leading dimension ldu on the device, ...) */
+int propack_b200_solver_local_rows(int solver, int* m_local, int* n_local, long* ldu, long* ldv);
+
 int propack_b200_init(void);                         /* create the context on the current device; 0 or negative */
 int propack_b200_set_stream(void* cuda_stream);      /* run on a caller stream (e.g. torch's current stream) */
 int propack_b200_set_lapack(const char* path);       /* shared object providing {d,s}bdsqr / {d,s}bdsdc */

@@ -136,6 +136,61 @@ template <class T> int csr_create(int m, int n, const int* rowptr, const int* co
   PB_API_CATCH(return code__)
 }
 
+// Row-sharded CSR: `row_*` = CSR of this rank's row block A[r0:r1, :] (global column ids), `colt_*` = CSR
+// of the transpose of this rank's column block, (A[:, c0:c1])^T, i.e. (c1-c0) rows x mg columns (global row ids) --
+// scipy: A[r0:r1].tocsr() and A[:, c0:c1].tocsc().  Bounds follow shard_bounds(); values are not conjugated.
+template <class T>
+int csr_create_sharded(int mg, int ng, const int* row_rp, const int* row_ci, const void* row_va_, const int* colt_rp,
+                       const int* colt_ci, const void* colt_va_, int base) {
+  PB_API_TRY
+  Context::get();
+  Comm& cm = Comm::get();
+  const T* row_va = static_cast<const T*>(row_va_);
+  const T* colt_va = static_cast<const T*>(colt_va_);
+  if (mg <= 0 || ng <= 0 || !row_rp || !colt_rp) throw std::runtime_error("propack_b200: bad sharded CSR arguments");
+  long r0, r1, c0, c1;
+  shard_bounds(mg, cm.world, cm.rank, r0, r1);
+  shard_bounds(ng, cm.world, cm.rank, c0, c1);
+  const int ml = (int)(r1 - r0), nl = (int)(c1 - c0);
+  auto op = std::make_shared<ShardedCsrOperator<T>>();
+  op->m = ml; op->n = nl; op->mg = mg; op->ng = ng; op->m_off = r0; op->n_off = c0;
+  op->ld_m = shard_slice(mg, cm.world); op->ld_n = shard_slice(ng, cm.world);
+  op->sharded = true;
+  auto upload = [&](int rows, long width, const int* rp_in, const int* ci_in, const T* va_in, DeviceBuffer<int>& rp, DeviceBuffer<int>& ci,
+                    DeviceBuffer<T>& va, CsrDevice<T>& D, long cols_padded) {
+    std::vector<int> hrp(rows + 1);
+    for (int i = 0; i <= rows; ++i) hrp[i] = rp_in[i] - base;
+    if (hrp[0] != 0) throw std::runtime_error("propack_b200: sharded CSR row pointers must start at the index base");
+    const long nnz = hrp[rows];
+    std::vector<int> hci(std::max<long>(nnz, 1));
+    for (long p = 0; p < nnz; ++p) {
+      hci[p] = ci_in[p] - base;
+      if (hci[p] < 0 || hci[p] >= width) throw std::runtime_error("propack_b200: sharded CSR index out of range");
+    }
+    for (int i = 0; i < rows; ++i)
+      for (int p = hrp[i] + 1; p < hrp[i + 1]; ++p)
+        if (hci[p - 1] > hci[p]) throw std::runtime_error("propack_b200: CSR indices must be sorted within each row");
+    rp.alloc(rows + 1); ci.alloc(std::max<long>(nnz, 1)); va.alloc(std::max<long>(nnz, 1));
+    PB_CUDA(cudaMemcpy(rp.p, hrp.data(), sizeof(int) * (rows + 1), cudaMemcpyHostToDevice));
+    if (nnz) {
+      PB_CUDA(cudaMemcpy(ci.p, hci.data(), sizeof(int) * nnz, cudaMemcpyHostToDevice));
+      PB_CUDA(cudaMemcpy(va.p, va_in, sizeof(T) * nnz, cudaMemcpyHostToDevice));
+    }
+    fill_device_csr<T>(D, rows, (int)cols_padded, nnz, rp, ci, va);
+  };
+  upload(ml, ng, row_rp, row_ci, row_va, op->rp, op->ci, op->va, op->A, op->ld_n * cm.world);
+  upload(nl, mg, colt_rp, colt_ci, colt_va, op->trp, op->tci, op->tva, op->At, op->ld_m * cm.world);
+  op->xfull_n.alloc((size_t)op->ld_n * cm.world);
+  op->xfull_m.alloc((size_t)op->ld_m * cm.world);
+  PB_CUDA(cudaMemset(op->xfull_n.p, 0, sizeof(T) * op->xfull_n.n));
+  PB_CUDA(cudaMemset(op->xfull_m.p, 0, sizeof(T) * op->xfull_m.n));
+  OpEntry e; e.tag = abi<T>::tag; e.kind = 2; e.op = op;
+  const int h = g_next_op++;
+  g_ops[h] = e;
+  return h;
+  PB_API_CATCH(return code__)
+}
+
 template <class T> int dense_create(int m, int n, const void* A_, long lda, bool adopt_device) {
   PB_API_TRY
   Context& c = Context::get();
@@ -469,7 +524,13 @@ extern "C" {
   int propack_b200_csr_create_##P(int m, int n, const int* rowptr, const int* colind, const CT* values, int index_base) {        \
     return csr_create<T>(m, n, rowptr, colind, values, index_base);                                                              \
   }                                                                                                                              \
-  int propack_b200_dense_create_##P(int m, int n, const CT* A, long lda) { return dense_create<T>(m, n, A, lda, false); }
+  int propack_b200_dense_create_##P(int m, int n, const CT* A, long lda) { return dense_create<T>(m, n, A, lda, false); } \
+  int propack_b200_csr_create_sharded_##P(int m_global, int n_global, const int* row_rowptr, const int* row_colind,             \
+                                          const CT* row_values, const int* colt_rowptr, const int* colt_rowind,                  \
+                                          const CT* colt_values, int index_base) {                                               \
+    return csr_create_sharded<T>(m_global, n_global, row_rowptr, row_colind, row_values, colt_rowptr, colt_rowind, colt_values,  \
+                                 index_base);                                                                                    \
+  }
 
 PB_DRIVERS_REAL(s, float, float, pb200_aprod_s_t)
 PB_DRIVERS_REAL(d, double, double, pb200_aprod_d_t)
@@ -652,6 +713,51 @@ int propack_b200_solver_get_v(int solver, int ncols, void* V_host, long ldv) {
     auto* e = static_cast<Engine<T>*>(s.engine.get());
     download_cols<T>(e->c, V_host, ldv, e->V, e->ldv, e->n, std::min(ncols, e->vcols));
     e->c.sync();
+    return 0;
+  });
+  PB_API_CATCH(return code__)
+}
+
+// ---- multi-GPU (one process per GPU) -------------------------------------------------------------------------------
+int propack_b200_comm_unique_id(void* id128_out) {
+  PB_API_TRY
+  Comm::unique_id(id128_out);
+  return 0;
+  PB_API_CATCH(return code__)
+}
+int propack_b200_comm_init(int rank, int world, const void* id128) {
+  PB_API_TRY
+  Context::get();  // binds the device first
+  Comm::get().init(rank, world, id128);
+  return 0;
+  PB_API_CATCH(return code__)
+}
+int propack_b200_comm_finalize(void) {
+  PB_API_TRY
+  Comm::get().finalize();
+  return 0;
+  PB_API_CATCH(return code__)
+}
+int propack_b200_comm_rank(void) { return Comm::get().rank; }
+int propack_b200_comm_world(void) { return Comm::get().world; }
+long propack_b200_shard_slice(long dim, int world) { return shard_slice(dim, world); }
+void propack_b200_shard_bounds(long dim, int world, int rank, long* lo, long* hi) { shard_bounds(dim, world, rank, *lo, *hi); }
+void propack_b200_comm_stats(long long* n_allreduce, long long* n_allgather, double* allgather_bytes) {
+  Comm& cm = Comm::get();
+  if (n_allreduce) *n_allreduce = cm.n_allreduce;
+  if (n_allgather) *n_allgather = cm.n_allgather;
+  if (allgather_bytes) *allgather_bytes = cm.allgather_bytes;
+}
+int propack_b200_solver_local_rows(int solver, int* m_local, int* n_local, long* ldu, long* ldv) {
+  PB_API_TRY
+  SolverEntry& s = find_solver(solver);
+  return dispatch(s.tag, [&](auto* t) {
+    using T = std::remove_pointer_t<decltype(t)>;
+    auto* e = static_cast<Engine<T>*>(s.engine.get());
+    if (m_local) *m_local = e->m;
+    if (n_local) *n_local = e->n;
+    if (ldu) *ldu = e->ldu;
+    if (ldv) *ldv = e->ldv;
     return 0;
   });
   PB_API_CATCH(return code__)

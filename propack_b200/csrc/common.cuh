@@ -162,6 +162,8 @@ struct ReduceWs {              // workspace of one in-flight grid reduction
   ScalarSlot* dev_slot;        // device copy of the result
   ScalarSlot* host_slot;       // mapped pinned copy (device address)
   unsigned long long seq;      // sequence number this launch publishes
+  int local_only;              // row-sharded run: store this rank's raw partial in dev_slot only; the host-side
+                               // Context::complete_reduce() all-reduces it across ranks and publishes
 };
 
 // Called by every thread of every CTA; `v` = this CTA's partial (valid in thread 0; real part
@@ -187,14 +189,19 @@ __device__ inline void grid_publish(double vre, double vim, const ReduceWs& ws, 
   sr = block_sum(sr, red_smem);
   si = block_sum(si, red_smem);
   if (threadIdx.x == 0) {
-    if (kind == 1) sr = sqrt(sr);
-    ws.dev_slot->re = sr; ws.dev_slot->im = si;
-    ws.host_slot->re = sr; ws.host_slot->im = si;
-    __threadfence_system();
-    ws.host_slot->seq = ws.seq;
+    if (ws.local_only) {
+      ws.dev_slot->re = sr; ws.dev_slot->im = si;
+    } else {
+      if (kind == 1) sr = sqrt(sr);
+      ws.dev_slot->re = sr; ws.dev_slot->im = si;
+      ws.host_slot->re = sr; ws.host_slot->im = si;
+      __threadfence_system();
+      ws.host_slot->seq = ws.seq;
+    }
     *ws.ticket = 0u;
   }
 }
+
 
 constexpr int kThreads = 256;   // CTA size of the streaming kernels
 constexpr int kMaxCtas = 4096;  // upper bound on any grid that uses grid_publish

@@ -1,5 +1,7 @@
 #include "context.hpp"
 
+#include "comm.hpp"
+
 #include <cstdlib>
 #include <cstring>
 
@@ -63,6 +65,25 @@ double Context::wait(const Pending& p, double* imag) {
   }
   if (imag) *imag = s->im;
   return s->re;
+}
+
+// Second half of a cross-rank reduction: after the all-reduce of (re, im) in dev_slot, apply the norm's sqrt and
+// publish to the host-mapped slot.
+__global__ void publish_slot_kernel(ScalarSlot* dev_slot, ScalarSlot* host_slot, unsigned long long seq, int kind) {
+  double sr = dev_slot->re, si = dev_slot->im;
+  if (kind == 1) { sr = sqrt(sr); dev_slot->re = sr; }
+  host_slot->re = sr; host_slot->im = si;
+  __threadfence_system();
+  host_slot->seq = seq;
+}
+
+void Context::complete_reduce(const Pending& p, int kind) {
+  if (!p.local_only) return;
+  ScalarSlot* d = dev_slots + p.slot;
+  Comm::get().allreduce_sum(&d->re, 2, stream);   // (re, im) are adjacent doubles
+  publish_slot_kernel<<<1, 1, 0, stream>>>(d, host_slots_dev + p.slot, p.seq, kind);
+  PB_LAUNCH_CHECK();
+  ctr.launches += 1;
 }
 
 void* Context::scratch(size_t bytes) {

@@ -45,16 +45,23 @@ class Context {
   unsigned long long seq = 0;
   int next_slot = 0;
 
-  struct Pending { int slot; unsigned long long seq; };
+  struct Pending { int slot; unsigned long long seq; int local_only = 0; };
+  // Row-sharded runs (one process per GPU): while set, every reduction a kernel publishes is this rank's partial
+  // and is completed across ranks (Comm all-reduce) before the host sees it.  Set by Engine for sharded operators.
+  bool dist_reduce = false;
   // Allocate a result slot for the next reducing kernel.
   ReduceWs new_reduce(Pending* p) {
     int s = next_slot; next_slot = (next_slot + 1) % kSlots;
     ReduceWs ws;
     ws.partials = partials; ws.ticket = ticket;
     ws.dev_slot = dev_slots + s; ws.host_slot = host_slots_dev + s; ws.seq = ++seq;
-    p->slot = s; p->seq = ws.seq;
+    ws.local_only = dist_reduce ? 1 : 0;
+    p->slot = s; p->seq = ws.seq; p->local_only = ws.local_only;
     return ws;
   }
+  // Call right after launching the kernel that owns `p`.  kind: 0 = sum (dot products), 1 = sqrt(sum) (norms).
+  // Single-GPU: nothing to do (the kernel's last CTA already published).
+  void complete_reduce(const Pending& p, int kind);
   const ScalarSlot* dev_slot(const Pending& p) const { return dev_slots + p.slot; }
   // Spin until the kernel that owns `p` has published; returns the real part (imag via out param).
   double wait(const Pending& p, double* imag = nullptr);

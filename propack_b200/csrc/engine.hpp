@@ -12,6 +12,7 @@
 #include <stdexcept>
 #include <vector>
 
+#include "comm.hpp"
 #include "context.hpp"
 #include "host_algebra.hpp"
 #include "host_lapack.hpp"
@@ -36,7 +37,14 @@ template <class R> inline cplx<R> neg(cplx<R> a) { return cplx<R>(-a.x, -a.y); }
 // ------------------------------------------------------------------------------------------------
 template <class T> struct LinOp {
   using R = real_t<T>;
-  int m = 0, n = 0;
+  int m = 0, n = 0;            // rows / columns held by THIS process (= the global sizes on one GPU)
+  // row-sharded operators (one process per GPU): global sizes, this rank's first global row / column,
+  // and the common slice lengths that the engine must use as leading dimensions of U and V
+  int mg = 0, ng = 0;
+  long m_off = 0, n_off = 0, ld_m = 0, ld_n = 0;
+  bool sharded = false;
+  int global_m() const { return sharded ? mg : m; }
+  int global_n() const { return sharded ? ng : n; }
   virtual ~LinOp() {}
   virtual void apply(Context& c, bool adjoint, const T* x, T* y, R coef, const T* prev, Pending* nrm) = 0;
   virtual double algorithmic_bytes(bool adjoint) const = 0;  // per apply, SURVEY 8d byte model
@@ -55,6 +63,33 @@ template <class T> struct CsrOperator : LinOp<T> {
     const double w = sizeof(T);
     const double rows = adjoint ? this->n : this->m, cols = adjoint ? this->m : this->n;
     return (double)A.nnz * (w + 4) + (rows + 1) * 4 + cols * w + rows * w;
+  }
+};
+
+// Row-sharded CSR operator: this rank holds the CSR of its row block of A (m_loc x ng) and the CSR of the transpose
+// of its column block (n_loc x mg), so BOTH products are "all-gather the input vector, then a local gather-SpMV":
+// no cross-rank summation inside a matvec, and every output element is produced by the same kernel in the same
+// order as on one GPU.  Slices are contiguous and of equal padded length, so global column indices address the
+// gathered vector directly.
+template <class T> struct ShardedCsrOperator : LinOp<T> {
+  using R = real_t<T>;
+  DeviceBuffer<int> rp, ci, trp, tci;
+  DeviceBuffer<T> va, tva, xfull_n, xfull_m;
+  CsrDevice<T> A, At;  // A: m_loc x (world*ld_n);  At: n_loc x (world*ld_m)
+  void apply(Context& c, bool adjoint, const T* x, T* y, R coef, const T* prev, Pending* nrm) override {
+    Comm& cm = Comm::get();
+    if (adjoint) {
+      cm.allgather(x, xfull_m.p, sizeof(T) * (size_t)this->ld_m, c.stream);
+      k_spmv<T>(c, At, /*conj=*/true, xfull_m.p, y, coef, prev, nrm);
+    } else {
+      cm.allgather(x, xfull_n.p, sizeof(T) * (size_t)this->ld_n, c.stream);
+      k_spmv<T>(c, A, false, xfull_n.p, y, coef, prev, nrm);
+    }
+  }
+  double algorithmic_bytes(bool adjoint) const override {
+    const double w = sizeof(T);
+    const CsrDevice<T>& M = adjoint ? At : A;
+    return (double)M.nnz * (w + 4) + ((double)M.rows + 1) * 4 + (double)M.cols * w + (double)M.rows * w;
   }
 };
 
@@ -107,7 +142,9 @@ template <class T> class Engine {
   using R = real_t<T>;
   Context& c;
   LinOp<T>* op;
-  int m, n;
+  int m, n;           // local vector lengths (this rank's rows of U / V)
+  int mg, ng;         // global problem size (what the reference's formulas see)
+  bool dist;          // row-sharded run: reductions are completed across ranks
   long ldu, ldv;      // padded leading dimensions (multiples of 32 elements => 256-byte aligned columns)
   int ucols, vcols;   // allocated columns
   DeviceBuffer<T> Ubuf, Vbuf, wrk, hbuf;
@@ -116,7 +153,9 @@ template <class T> class Engine {
   static long pad_ld(long rows) { return (rows + 31) / 32 * 32; }
 
   Engine(Context& ctx, LinOp<T>* op_, int ucols_, int vcols_)
-      : c(ctx), op(op_), m(op_->m), n(op_->n), ldu(pad_ld(op_->m)), ldv(pad_ld(op_->n)), ucols(ucols_), vcols(vcols_) {
+      : c(ctx), op(op_), m(op_->m), n(op_->n), mg(op_->global_m()), ng(op_->global_n()),
+        dist(op_->sharded && Comm::get().active()), ldu(op_->ld_m > 0 ? op_->ld_m : pad_ld(op_->m)),
+        ldv(op_->ld_n > 0 ? op_->ld_n : pad_ld(op_->n)), ucols(ucols_), vcols(vcols_) {
     Ubuf.alloc((size_t)ldu * ucols);
     Vbuf.alloc((size_t)ldv * vcols);
     wrk.alloc((size_t)std::max(ldu, ldv));
@@ -127,6 +166,12 @@ template <class T> class Engine {
     PB_CUDA(cudaMemsetAsync(V, 0, sizeof(T) * (size_t)ldv * vcols, c.stream));
     PB_CUDA(cudaMemsetAsync(wrk.p, 0, sizeof(T) * wrk.n, c.stream));
   }
+  // While alive, kernels launched through this engine publish cross-rank reductions (no-op on one GPU).
+  struct DistScope {
+    Context& c; bool old;
+    DistScope(Context& c_, bool on) : c(c_), old(c_.dist_reduce) { c.dist_reduce = on; }
+    ~DistScope() { c.dist_reduce = old; }
+  };
   T* ucol(int j) { return U + (size_t)(j - 1) * ldu; }  // 1-based column
   T* vcol(int j) { return V + (size_t)(j - 1) * ldv; }
 
@@ -198,9 +243,12 @@ template <class T> class Engine {
     k_zero<T>(c, len, vnew);
     c.ctr.nreorth += 1;
   }
-  // hook for the row-sharded multi-GPU build: all-reduce of the l coefficients
-  std::function<void(T*, int)> allreduce_coeffs;
-  void reduce_coefficients(int l) { if (allreduce_coeffs) allreduce_coeffs(hbuf.p, l); }
+  // row-sharded run: all-reduce of the l coefficients h = V_local^H q_local (the OpenMP build's CRITICAL
+  // sum over threads, dreorth.F:177-197)
+  void reduce_coefficients(int l) {
+    if (!dist) return;
+    Comm::get().allreduce_sum(reinterpret_cast<R*>(hbuf.p), (size_t)l * (scalar_traits<T>::is_complex ? 2 : 1), c.stream);
+  }
 
   // --- dgetu0 (dgetu0.F:11-89) ---------------------------------------------------------------------------
   // u0 <- op(A) r, r ~ LAPACK uniform(-1,1) stream from iseed (1,3,5,7) (reset on every call), then
@@ -208,13 +256,14 @@ template <class T> class Engine {
   void getu0(bool adjoint, int j, int ntry, T* u0, R& u0norm, const T* basis, long ld, int& ierr, int icgs, R& anormest) {
     Context::PhaseScope ps(c, PH_GETU0);
     const R kappa = R(0.717f);  // single-precision literal in dgetu0.F:28-29
-    const long rsize = adjoint ? m : n, usize = adjoint ? n : m;
+    const long rsize = adjoint ? m : n, usize = adjoint ? n : m;          // local lengths
+    const long rglobal = adjoint ? mg : ng, roff = adjoint ? op->m_off : op->n_off;
     int iseed[4] = {1, 3, 5, 7};
     ierr = 0;
     for (int itry = 0; itry < ntry; ++itry) {
       // stream position: itry-th block of rsize values (dlarnv keeps advancing iseed between tries)
       Pending pr, pu;
-      advance_and_draw(iseed, rsize, wrk.p, &pr);
+      advance_and_draw(iseed, rsize, rglobal, roff, wrk.p, &pr);
       const R nrm = (R)c.wait(pr);
       op->apply(c, adjoint, wrk.p, u0, R(0), nullptr, &pu);
       c.ctr.nopx += 1;
@@ -229,13 +278,14 @@ template <class T> class Engine {
     }
     ierr = -1;
   }
-  // draw `len` values starting at the current seed and advance the seed past them, like xLARNV
-  void advance_and_draw(int iseed[4], long len, T* x, Pending* p) {
-    k_larnv_nrm<T>(c, len, x, iseed, p);
+  // draw this rank's `len` values (global positions off .. off+len-1) of the stream that starts at the current seed
+  // and advance the seed past all `glen` values, like xLARNV
+  void advance_and_draw(int iseed[4], long len, long glen, long off, T* x, Pending* p) {
+    k_larnv_nrm<T>(c, len, x, iseed, p, off);
     const unsigned long long M = (1ull << 48) - 1;
     unsigned long long s = ((unsigned long long)iseed[0] << 36) | ((unsigned long long)iseed[1] << 24) |
                            ((unsigned long long)iseed[2] << 12) | (unsigned long long)iseed[3];
-    unsigned long long e = (unsigned long long)len * (scalar_traits<T>::is_complex ? 2 : 1), base = 33952834046453ull, r = 1;
+    unsigned long long e = (unsigned long long)glen * (scalar_traits<T>::is_complex ? 2 : 1), base = 33952834046453ull, r = 1;
     while (e) { if (e & 1) r = (r * base) & M; base = (base * base) & M; e >>= 1; }
     s = (s * r) & M;
     iseed[0] = int((s >> 36) & 4095); iseed[1] = int((s >> 24) & 4095); iseed[2] = int((s >> 12) & 4095); iseed[3] = int(s & 4095);

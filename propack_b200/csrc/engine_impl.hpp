@@ -16,8 +16,9 @@ template <class T> int Engine<T>::lanbpro(int k0, int& k, R* a, R* b, R& rnorm, 
   const R zero = 0, one = 1, FUDGE = R(1.01), kappa = R(0.717);
   const R eps = host::Machine<R>::eps;
   const R eps34 = std::pow(eps, R(0.75));
-  const R epsn = R(std::max(m, n)) * eps;
-  const R epsn2 = std::sqrt(R(std::max(m, n))) * eps;
+  DistScope ds(c, dist);
+  const R epsn = R(std::max(mg, ng)) * eps;
+  const R epsn2 = std::sqrt(R(std::max(mg, ng))) * eps;
   const bool elr = ioption[1] > 0;
   const int cgs = ioption[0];
   int ierr = 0;
@@ -214,10 +215,11 @@ template <class T> int Engine<T>::lanbpro(int k0, int& k, R* a, R* b, R& rnorm, 
 // ================================================================================================
 template <class T> void Engine<T>::ritzvec(bool smallest, bool jobu, bool jobv, int k, int dim, R* D, R* E) {
   Context::PhaseScope ps(c, PH_RITZ);
+  DistScope ds(c, dist);
   std::vector<R> Mt((size_t)(dim + 1) * (dim + 1), R(0)), Qt((size_t)dim * dim, R(0)), P((size_t)dim * dim, R(0));
   R c1 = 0, c2 = 0;
   int info = 0;
-  host::bidiag_qr(dim == std::min(m, n), jobu, dim, D, E, c1, c2, Mt.data(), dim + 1);  // dritzvec.F:116
+  host::bidiag_qr(dim == std::min(mg, ng), jobu, dim, D, E, c1, c2, Mt.data(), dim + 1);  // dritzvec.F:116
   host::bdsdc_full(dim, D, E, P.data(), dim, Qt.data(), dim, &info);                    // :123
   const int mstart = smallest ? dim - k : 0;  // 0-based first wanted row of X / Q^T
   if (jobu) {
@@ -252,8 +254,9 @@ int Engine<T>::lansvd(bool jobu, bool jobv, int& k, int kmax, R* sigma, R* bnd, 
   const R one = 1, zero = 0;
   const R eps = host::Machine<R>::eps;
   const R eps34 = std::pow(eps, R(0.75));
-  const R epsn = R(std::max(m, n)) * eps / R(2);
-  const int lanmax = std::min(std::min(n + 1, m + 1), kmax);
+  DistScope ds(c, dist);
+  const R epsn = R(std::max(mg, ng)) * eps / R(2);
+  const int lanmax = std::min(std::min(ng + 1, mg + 1), kmax);
   const R tol = std::min(one, std::max(R(16) * eps, tolin));
   if (lanmax + 1 > ucols || lanmax > vcols) throw std::runtime_error("propack_b200: basis buffers smaller than kmax");
   std::vector<R> a(lanmax + 1, zero), b(lanmax + 1, zero), th(lanmax + 1), ee(lanmax + 1), wb(lanmax + 2, zero);
@@ -275,12 +278,12 @@ int Engine<T>::lansvd(bool jobu, bool jobv, int& k, int kmax, R* sigma, R* bnd, 
       std::copy(b.begin(), b.begin() + j, ee.begin());
       std::fill(wb.begin(), wb.begin() + j + 1, zero);
       int lapinfo = 0;
-      host::bidiag_qr<R>(j == std::min(m, n), false, j, th.data(), ee.data(), wb[j - 1], wb[j], nullptr, 0);
+      host::bidiag_qr<R>(j == std::min(mg, ng), false, j, th.data(), ee.data(), wb[j - 1], wb[j], nullptr, 0);
       host::bdsqr_row(j, th.data(), ee.data(), wb.data(), &lapinfo);
       c.ctr.nbsvd += 1;
       anorm = (j > 5) ? th[0] : std::max(anorm, th[0]);
       for (int i = 0; i < j; ++i) wb[i] = std::fabs(rnorm * wb[i]);
-      host::refine_bounds(std::min(m, n), j, th.data(), wb.data(), epsn * anorm, eps34);
+      host::refine_bounds(std::min(mg, ng), j, th.data(), wb.data(), epsn * anorm, eps34);
       for (int i = 0; i < std::min(j, k); ++i) bnd[i] = wb[i];
       neig = 0;  // leading converged values only (:222-236)
       for (int i = 0; i < std::min(j, k); ++i) {
@@ -313,8 +316,9 @@ int Engine<T>::lansvd_irl(bool smallest, bool jobu, bool jobv, int& dim, int p, 
   const R one = 1, zero = 0;
   const R eps = host::Machine<R>::eps;
   const R eps34 = std::pow(eps, R(0.75));
-  const R epsn = R(std::max(m, n)) * eps / R(2);
-  dim = std::min(dim, std::min(n + 1, m + 1));  // dlansvd_irl.F:170
+  DistScope ds(c, dist);
+  const R epsn = R(std::max(mg, ng)) * eps / R(2);
+  dim = std::min(dim, std::min(ng + 1, mg + 1));  // dlansvd_irl.F:170
   const int k = dim - p;
   const R tol = std::min(one, std::max(R(16) * eps, tolin));
   if (dim + 1 > ucols || dim > vcols) throw std::runtime_error("propack_b200: basis buffers smaller than dim");
@@ -335,12 +339,12 @@ int Engine<T>::lansvd_irl(bool smallest, bool jobu, bool jobv, int& dim, int p, 
       std::copy(b.begin(), b.begin() + dim, ee.begin());
       std::fill(wb.begin(), wb.begin() + dim + 1, zero);
       int lapinfo = 0;
-      host::bidiag_qr<R>(dim == std::min(m, n), false, dim, th.data(), ee.data(), wb[dim - 1], wb[dim], nullptr, 0);
+      host::bidiag_qr<R>(dim == std::min(mg, ng), false, dim, th.data(), ee.data(), wb[dim - 1], wb[dim], nullptr, 0);
       host::bdsqr_row(dim, th.data(), ee.data(), wb.data(), &lapinfo);
       c.ctr.nbsvd += 1;
       anorm = (dim > 5) ? th[0] : std::max(anorm, th[0]);
       for (int i = 0; i < dim; ++i) wb[i] = std::fabs(rnorm * wb[i]);
-      host::refine_bounds(std::min(m, n), smallest ? dim : std::min(dim, neig), th.data(), wb.data(), epsn * anorm, eps34);
+      host::refine_bounds(std::min(mg, ng), smallest ? dim : std::min(dim, neig), th.data(), wb.data(), epsn * anorm, eps34);
       nconv = 0;  // :262-290
       if (smallest) {
         for (int i = dim - neig; i < dim; ++i)

@@ -274,6 +274,7 @@ void k_gemv_n(Context& c, long L, int l, const T* V, long ldv, const T* h, real_
       gemv_n_kernel<T, false><<<grid, kThreads, smem, c.stream>>>(L, lc, V + (long)c0 * ldv, ldv, h + c0, cin_c, in_c, out, ws, want);
     PB_LAUNCH_CHECK();
     c.ctr.launches += 1;
+    if (want) c.complete_reduce(*nrm, 1);
     c0 += lc;
   } while (c0 < l);
 }

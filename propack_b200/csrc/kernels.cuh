@@ -23,8 +23,9 @@ template <class T> void k_dotc(Context& c, long n, const T* x, const T* y, Pendi
 // publish ||x||_2                                                (pdnrm2 dblasext.F:6)
 template <class T> void k_nrm2(Context& c, long n, const T* x, Pending* out);
 template <class T> void k_zero(Context& c, long n, T* x);          // pdzero dblasext.F:202
-// x(i) <- LAPACK xLARNV(idist=2, iseed) stream element i, i=0..n-1 ; publish ||x||  (dgetu0.F:69-70)
-template <class T> void k_larnv_nrm(Context& c, long n, T* x, const int iseed[4], Pending* nrm);
+// x(i) <- LAPACK xLARNV(idist=2, iseed) stream element offset+i, i=0..n-1 ; publish ||x||  (dgetu0.F:69-70).
+// `offset` = global index of this rank's first element in a row-sharded run (0 on one GPU).
+template <class T> void k_larnv_nrm(Context& c, long n, T* x, const int iseed[4], Pending* nrm, long offset = 0);
 
 // --- tall-skinny GEMV pair (reference: dcgs, double/dreorth.F:174 and :199-205) --------------------
 // h(0:l) <- V(:,0:l)^H q   (column-major V, leading dim ldv, L rows).  h is a device buffer.

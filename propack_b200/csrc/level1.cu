@@ -4,6 +4,8 @@
 // pdzero :202), dsafescal.F:4-55, and dgetu0.F:66-70 (dlarnv(idist=2, iseed=(1,3,5,7)) + pdnrm2).
 // All are pure HBM streams; every vector access is a 128-bit pack, norms / dots are reduced in a
 // fixed order and published by the last CTA (common.cuh: grid_publish).
+#include <algorithm>
+
 #include "kernels.cuh"
 
 namespace pb {
@@ -124,7 +126,7 @@ template <class R> __device__ inline void larnv_elem(cplx<R>& out, unsigned long
 
 template <class T>
 __global__ void __launch_bounds__(kThreads)
-larnv_kernel(long n, T* __restrict__ x, unsigned long long s0, ReduceWs ws) {
+larnv_kernel(long n, T* __restrict__ x, unsigned long long s0, long offset, ReduceWs ws) {
   constexpr int VEC = Pack<T>::N;
   __shared__ double red[32];
   const long np = (n + VEC - 1) / VEC;
@@ -134,7 +136,7 @@ larnv_kernel(long n, T* __restrict__ x, unsigned long long s0, ReduceWs ws) {
 #pragma unroll
     for (int e = 0; e < VEC; ++e) {
       const long idx = i * VEC + e;
-      if (idx < n) larnv_elem(p.v[e], s0, idx);
+      if (idx < n) larnv_elem(p.v[e], s0, offset + idx);
       else p.v[e] = zero_<T>();
       sr += (double)abs2_(p.v[e]);
     }
@@ -144,7 +146,7 @@ larnv_kernel(long n, T* __restrict__ x, unsigned long long s0, ReduceWs ws) {
   grid_publish(tr, 0.0, ws, 1, red);
 }
 
-template <class T> int l1_grid(Context& c, long n) {
+template <class T> int l1_grid(Context& c, long n) {  // >= 1 CTA even for n = 0 (a rank that owns no rows still publishes)
   return c.grid_for((n + Pack<T>::N - 1) / Pack<T>::N, kThreads * L1_S, 8);
 }
 
@@ -173,26 +175,30 @@ template <class T> void k_axpy_nrm(Context& c, long n, T a, const T* x, T* y, Pe
   reduce_kernel<T, 0><<<l1_grid<T>(c, n), kThreads, 0, c.stream>>>(n, a, x, y, ws);
   PB_LAUNCH_CHECK();
   c.ctr.launches += 1;
+  c.complete_reduce(*nrm, 1);
 }
 template <class T> void k_dotc(Context& c, long n, const T* x, const T* y, Pending* out) {
   ReduceWs ws = c.new_reduce(out);
   reduce_kernel<T, 1><<<l1_grid<T>(c, n), kThreads, 0, c.stream>>>(n, zero_<T>(), x, const_cast<T*>(y), ws);
   PB_LAUNCH_CHECK();
   c.ctr.launches += 1;
+  c.complete_reduce(*out, 0);
 }
 template <class T> void k_nrm2(Context& c, long n, const T* x, Pending* out) {
   ReduceWs ws = c.new_reduce(out);
   reduce_kernel<T, 2><<<l1_grid<T>(c, n), kThreads, 0, c.stream>>>(n, zero_<T>(), x, nullptr, ws);
   PB_LAUNCH_CHECK();
   c.ctr.launches += 1;
+  c.complete_reduce(*out, 1);
 }
-template <class T> void k_larnv_nrm(Context& c, long n, T* x, const int iseed[4], Pending* nrm) {
+template <class T> void k_larnv_nrm(Context& c, long n, T* x, const int iseed[4], Pending* nrm, long offset) {
   const unsigned long long s0 = ((unsigned long long)iseed[0] << 36) | ((unsigned long long)iseed[1] << 24) |
                                 ((unsigned long long)iseed[2] << 12) | (unsigned long long)iseed[3];
   ReduceWs ws = c.new_reduce(nrm);
-  larnv_kernel<T><<<l1_grid<T>(c, n), kThreads, 0, c.stream>>>(n, x, s0, ws);
+  larnv_kernel<T><<<l1_grid<T>(c, std::max<long>(n, 1)), kThreads, 0, c.stream>>>(n, x, s0, offset, ws);
   PB_LAUNCH_CHECK();
   c.ctr.launches += 1;
+  c.complete_reduce(*nrm, 1);
 }
 
 #define PB_INST(T)                                                                \
@@ -202,7 +208,7 @@ template <class T> void k_larnv_nrm(Context& c, long n, T* x, const int iseed[4]
   template void k_axpy_nrm<T>(Context&, long, T, const T*, T*, Pending*);         \
   template void k_dotc<T>(Context&, long, const T*, const T*, Pending*);          \
   template void k_nrm2<T>(Context&, long, const T*, Pending*);                    \
-  template void k_larnv_nrm<T>(Context&, long, T*, const int*, Pending*);
+  template void k_larnv_nrm<T>(Context&, long, T*, const int*, Pending*, long);
 PB_INST(float)
 PB_INST(double)
 PB_INST(cplx<float>)

@@ -174,6 +174,7 @@ void k_spmv(Context& c, const CsrDevice<T>& A, bool conj, const T* x, T* y, real
     spmv_kernel<T, false><<<grid, kThreads, 0, c.stream>>>(A, x, y, coef, prev, ws, want);
   PB_LAUNCH_CHECK();
   c.ctr.launches += 1;
+  if (nrm) c.complete_reduce(*nrm, 1);
 }
 
 // Lanes per row for a matrix with `nnz` non-zeros in `rows` rows: the largest row group (32/LPR rows) whose

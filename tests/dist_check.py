@@ -1,0 +1,97 @@
+#!/usr/bin/env python
+"""Multi-GPU parity check, one process per GPU:  torchrun --nproc-per-node N tests/dist_check.py
+
+Runs the row-sharded DLANSVD / ZLANSVD / DLANSVD_IRL on N GPUs and checks, on rank 0, against dense LAPACK SVD and
+the CPU oracle (test infrastructure): sigma to 1e-10 relative, residuals, orthogonality -- the same bars as the
+single-GPU driver tests.  Prints DIST_CHECK_OK on success.
+"""
+import os
+import sys
+
+import numpy as np
+import scipy.sparse as sp
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from propack_b200 import dist as pdist  # noqa: E402
+import propack_b200  # noqa: E402
+
+
+def relerr(a, b):
+    return float(np.max(np.abs(np.asarray(a) - np.asarray(b)) / np.abs(np.asarray(b))))
+
+
+def rand_sparse(rng, m, n, density, dtype):
+    A = sp.random_array((m, n), density=density, format="csr", rng=rng, data_sampler=rng.standard_normal)
+    if np.issubdtype(dtype, np.complexfloating):
+        B = sp.random_array((m, n), density=density, format="csr", rng=rng, data_sampler=rng.standard_normal)
+        A = A + 1j * B
+    A = sp.csr_array(A.astype(dtype))
+    A.sort_indices()
+    return A
+
+
+def run_case(name, A, k, kmax, rank, world, irl=None, tol=1e-12):
+    m, n = A.shape
+    dtype = A.dtype
+    u0 = np.random.default_rng(1).uniform(size=m).astype(dtype)
+    op = pdist.ShardedOperator(A, rank, world)
+    lanmax = min(m + 1, n + 1, kmax)
+    sv = pdist.Solver(op, lanmax + 1, lanmax)
+    sv.set_start(u0)
+    if irl is None:
+        r = sv.lansvd(k, kmax, tol=tol, cgs=True)
+    else:
+        r = sv.lansvd_irl("L", irl[0], irl[1], k, 200, tol=tol, cgs=True)
+    U = pdist.gather_rows(r["U"], m)
+    V = pdist.gather_rows(r["V"], n)
+    ok = True
+    if rank == 0:
+        S = r["sigma"]
+        sd = np.linalg.svd(A.toarray(), compute_uv=False)[:k]
+        eps = np.finfo(dtype).eps
+        e_sig = relerr(S, sd)
+        res = float(np.max(np.linalg.norm(A @ V - U * S, axis=0)))
+        orth = float(max(np.max(np.abs(U.conj().T @ U - np.eye(k))), np.max(np.abs(V.conj().T @ V - np.eye(k)))))
+        # the CPU oracle on the same inputs (same start vector): parity of the algorithm, not only of the answer
+        from oracle import oracle_py as O
+        if irl is None:
+            ref = O.lansvd(A, k, kmax, tol=tol, u0=u0, cgs=True, dtype=dtype)
+        else:
+            ref = O.lansvd_irl(A, k, irl[0], p=irl[1], which="L", maxiter=200, tol=tol, u0=u0, cgs=True, dtype=dtype)
+        e_ref = relerr(S, ref["sigma"][:k]) if ref["k"] >= k else float("nan")
+        ok = (r["info"] == 0 and r["k"] == k and e_sig < 1e-10 and res < 1e-8 * S[0] and orth < 200 * np.sqrt(eps)
+              and (np.isnan(e_ref) or e_ref < 1e-10))
+        print(f"[dist_check] {name}: world={world} info={r['info']} k={r['k']} sigma_relerr_dense={e_sig:.2e} "
+              f"sigma_relerr_oracle={e_ref:.2e} max_residual={res:.2e} orth={orth:.2e} -> {'ok' if ok else 'FAIL'}", flush=True)
+    sv.close(); op.close()
+    flag = torch.tensor([1 if ok else 0], device="cuda")
+    dist.broadcast(flag, src=0)
+    return bool(flag.item())
+
+
+def main():
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    rank, world = pdist.init_comm()
+    rng = np.random.default_rng(0)
+    ok = True
+    ok &= run_case("d 3000x2000 lansvd", rand_sparse(rng, 3000, 2000, 0.005, np.float64), 8, 150, rank, world)
+    ok &= run_case("d 500x4100 lansvd (fat)", rand_sparse(rng, 500, 4100, 0.01, np.float64), 6, 120, rank, world)
+    ok &= run_case("d 4000x40 lansvd (ranks without columns)", rand_sparse(rng, 4000, 40, 0.2, np.float64), 5, 41, rank, world)
+    ok &= run_case("z 1500x1200 zlansvd", rand_sparse(rng, 1500, 1200, 0.01, np.complex128), 6, 150, rank, world)
+    ok &= run_case("d 3000x2000 lansvd_irl", rand_sparse(rng, 3000, 2000, 0.005, np.float64), 6, 60, rank, world, irl=(40, 20), tol=1e-10)
+    if rank == 0:
+        print("comm stats:", propack_b200.counters()["launches"], flush=True)
+        print("DIST_CHECK_OK" if ok else "DIST_CHECK_FAILED", flush=True)
+    pdist.finalize_comm()
+    dist.destroy_process_group()
+    sys.exit(0 if ok else 1)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,22 @@
+"""GPU (>= 2 devices): the row-sharded multi-GPU path under torchrun, checked against dense SVD and the oracle."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.gpu
+def test_row_sharded_drivers_two_gpus():
+    import torch
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs (run under `gpurun --gpus 2`)")
+    world = 2
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
+           "--master-port", "29517", os.path.join(ROOT, "tests", "dist_check.py")]
+    p = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=900)
+    sys.stdout.write(p.stdout[-4000:]); sys.stderr.write(p.stderr[-4000:])
+    assert p.returncode == 0 and "DIST_CHECK_OK" in p.stdout
