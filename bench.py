@@ -35,11 +35,16 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 WORKLOADS = {
-    # name: (m, n, density, k, kmax, tol)
+    # name: (m, n, density, k, kmax, tol)           DLANSVD (non-restarted), BASELINE configs[1] and reduced copies
     "c2": (1_000_000, 1_000_000, 1e-5, 50, 600, 1e-10),
     "c2-small": (100_000, 100_000, 1e-4, 50, 600, 1e-10),
     "c2-tiny": (20_000, 20_000, 5e-4, 10, 200, 1e-10),
+    # BASELINE configs[4] ("C5"): 10M x 10M, 10 distinct uniform columns per row (1e8 nnz), k=100, DLANSVD_IRL dim=300 p=200
+    "c5": (10_000_000, 10_000_000, None, 100, 300, 1e-10),
+    "c5-small": (1_000_000, 1_000_000, None, 100, 300, 1e-10),
 }
+IRL_P = {"c5": 200, "c5-small": 200}   # workloads solved with DLANSVD_IRL: shifts per restart (kmax column = dim)
+IRL_MAXITER = 50
 CPU_SAMPLE_STEPS = 150  # Lanczos steps of the same problem the CPU baseline runs per sample
 
 
@@ -47,7 +52,15 @@ def make_matrix(name):
     import scipy.sparse as sp
     m, n, dens, k, kmax, tol = WORKLOADS[name]
     rng = np.random.default_rng(0)
-    A = sp.random_array((m, n), density=dens, format="csr", rng=rng, data_sampler=rng.standard_normal)
+    if dens is None:   # exactly 10 uniform columns per row (the rare duplicates inside a row are summed)
+        per = 10
+        cols = rng.integers(0, n, size=(m, per), dtype=np.int32)
+        cols.sort(axis=1)
+        vals = rng.standard_normal(size=(m, per))
+        A = sp.csr_array((vals.ravel(), cols.ravel(), np.arange(0, m * per + 1, per, dtype=np.int64)), shape=(m, n))
+        A.sum_duplicates()
+    else:
+        A = sp.random_array((m, n), density=dens, format="csr", rng=rng, data_sampler=rng.standard_normal)
     A.sort_indices()
     u0 = np.random.default_rng(1).uniform(size=m)
     return A, u0, k, kmax, tol
@@ -163,10 +176,37 @@ def run_reference(args):
 
 
 def config_dict(name, A, k, kmax, tol):
-    return {"workload": f"BASELINE configs[1] '{name}': synthetic random CSR {A.shape[0]}x{A.shape[1]}, nnz={A.nnz} "
-                        f"(~{A.nnz / A.shape[0]:.1f}/row), k={k}, kmax={kmax}, tol={tol:g}, DLANSVD double, CGS, ELR",
-            "driver": "dlansvd", "k": k, "kmax": kmax, "tol": tol, "nnz": int(A.nnz), "rows": int(A.shape[0]),
-            "cols": int(A.shape[1]), "l2_policy": "inputs larger than L2 (no flush needed)"}
+    irl = name in IRL_P
+    which = "configs[4]" if irl else "configs[1]"
+    drv = f"DLANSVD_IRL double dim={kmax} p={IRL_P[name]}" if irl else f"kmax={kmax}, DLANSVD double"
+    return {"workload": f"BASELINE {which} '{name}': synthetic random CSR {A.shape[0]}x{A.shape[1]}, nnz={A.nnz} "
+                        f"(~{A.nnz / A.shape[0]:.1f}/row), k={k}, {drv}, tol={tol:g}, CGS, ELR",
+            "driver": "dlansvd_irl" if irl else "dlansvd", "k": k, "kmax": kmax, "tol": tol, "nnz": int(A.nnz),
+            "rows": int(A.shape[0]), "cols": int(A.shape[1]), "l2_policy": "inputs larger than L2 (no flush needed)"}
+
+
+def session_solve(L, solver, name, k, kmax, tol, jobu=1, jobv=1):
+    """One driver call on a solver session (DLANSVD, or DLANSVD_IRL for the restarted workloads). -> (sigma, k, info)"""
+    from propack_b200 import _lib
+    eps = np.finfo(np.float64).eps
+    sigma = np.zeros(k); bnd = np.zeros(k)
+    iopt = np.array([1, 1], dtype=np.int32)
+    info = C.c_int(0)
+    if name in IRL_P:
+        dopt = np.array([np.sqrt(eps), eps ** 0.75, 0.0, 0.002])
+        dim, neig = C.c_int(kmax), C.c_int(k)
+        _lib.check(L.propack_b200_solver_lansvd_irl(C.c_int(solver), C.c_int(0), C.c_int(jobu), C.c_int(jobv), C.byref(dim),
+                                                    C.c_int(IRL_P[name]), C.byref(neig), C.c_int(IRL_MAXITER),
+                                                    sigma.ctypes.data_as(C.c_void_p), bnd.ctypes.data_as(C.c_void_p), C.c_double(tol),
+                                                    dopt.ctypes.data_as(C.c_void_p), iopt.ctypes.data_as(C.c_void_p), C.byref(info)),
+                   "lansvd_irl")
+        return sigma[:neig.value], neig.value, info.value
+    dopt = np.array([np.sqrt(eps), eps ** 0.75, 0.0])
+    kk = C.c_int(k)
+    _lib.check(L.propack_b200_solver_lansvd(C.c_int(solver), C.c_int(jobu), C.c_int(jobv), C.byref(kk), C.c_int(kmax),
+                                            sigma.ctypes.data_as(C.c_void_p), bnd.ctypes.data_as(C.c_void_p), C.c_double(tol),
+                                            dopt.ctypes.data_as(C.c_void_p), iopt.ctypes.data_as(C.c_void_p), C.byref(info)), "lansvd")
+    return sigma[:kk.value], kk.value, info.value
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -197,19 +237,14 @@ def run_ours(args):
 
     def solve_resident():
         _lib.check(L.propack_b200_solver_set_start(C.c_int(solver), u0.ctypes.data_as(C.c_void_p)), "set_start")
-        sigma = np.zeros(k); bnd = np.zeros(k)
-        dopt = np.array([np.sqrt(eps), eps ** 0.75, 0.0]); iopt = np.array([1, 1], dtype=np.int32)
-        kk, info = C.c_int(k), C.c_int(0)
         propack_b200.reset_counters()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         torch.cuda.synchronize()
         e0.record(stream)
-        _lib.check(L.propack_b200_solver_lansvd(C.c_int(solver), C.c_int(1), C.c_int(1), C.byref(kk), C.c_int(kmax),
-                                                sigma.ctypes.data_as(C.c_void_p), bnd.ctypes.data_as(C.c_void_p), C.c_double(tol),
-                                                dopt.ctypes.data_as(C.c_void_p), iopt.ctypes.data_as(C.c_void_p), C.byref(info)), "lansvd")
+        sigma, kc, info = session_solve(L, solver, args.workload, k, kmax, tol)
         e1.record(stream)
         torch.cuda.synchronize()
-        return e0.elapsed_time(e1), propack_b200.counters(), sigma[:kk.value], kk.value, info.value
+        return e0.elapsed_time(e1), propack_b200.counters(), sigma, kc, info
 
     def barrier():
         if world > 1:
@@ -259,15 +294,24 @@ def run_ours(args):
     va = np.ascontiguousarray(A.data)
     pin = lambda a: torch.from_numpy(a).pin_memory().numpy()
     rp, ci, va, u0p = pin(rp), pin(ci), pin(va), pin(u0)
+    # caller-owned result buffers of the Fortran interface, in pinned memory (allocated once, outside the timed region)
+    Upin = torch.empty((k + 1, m), dtype=torch.float64).pin_memory().numpy().T
+    Vpin = torch.empty((k + 1, n), dtype=torch.float64).pin_memory().numpy().T
+
+    e2e_create = []
 
     def solve_e2e():
         t0 = time.perf_counter()
         op2 = f77.Operator.__new__(f77.Operator)
         h = _lib.check(L.propack_b200_csr_create_d(C.c_int(m), C.c_int(n), rp.ctypes.data_as(C.c_void_p), ci.ctypes.data_as(C.c_void_p),
                                                     va.ctypes.data_as(C.c_void_p), C.c_int(0)), "csr_create")
+        e2e_create.append(time.perf_counter() - t0)
         op2.handle, op2._cb, op2.dtype, op2.pfx, op2.shape = h, None, np.dtype(np.float64), "d", (m, n)
         op2.iparm = np.array([h, 0], dtype=np.int32); op2.parm = np.zeros(2)
-        r = f77.lansvd(op2, k, kmax, tol=tol, u0=u0p, cgs=True)
+        if args.workload in IRL_P:
+            r = f77.lansvd_irl(op2, k, kmax, p=IRL_P[args.workload], maxiter=IRL_MAXITER, tol=tol, u0=u0p, cgs=True, U=Upin, V=Vpin)
+        else:
+            r = f77.lansvd(op2, k, kmax, tol=tol, u0=u0p, cgs=True, U=Upin, V=Vpin)
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         op2.close()
@@ -309,7 +353,8 @@ def run_ours(args):
             "gpu_launches": int(launches), "host_syncs_per_solve": ctr["host_syncs"],
             "e2e": {"value": e2e_val, "unit": "steps/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "time_to_k_triplets_s": float(np.mean(e2e_t)),
-                    "path": "propack_b200_csr_create_d + dlansvd_ (Fortran ABI, pinned host CSR / start vector; U,V,sigma copied back)"},
+                    "operator_create_s": float(np.mean(e2e_create[1:])) if len(e2e_create) > 1 else None,
+                    "path": "propack_b200_csr_create_d + dlansvd[_irl]_ (Fortran ABI; host CSR, start vector and the caller's U,V result buffers in pinned memory; U,V,sigma copied back)"},
             "roofline": {"bound": "hbm", "kernel": "reorthogonalisation GEMV pair (gemv_t_kernel + gemv_t_finalize + gemv_n_kernel)",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
                          "frac_of_nominal_8000": achieved / 8000.0, "traffic": None,
@@ -327,6 +372,115 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def run_ours_sharded(args):
+    """N > 1: the same workload, row-sharded over the N GPUs of the node (strong scaling)."""
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    import propack_b200
+    from propack_b200 import _lib, dist as pdist
+    L = _lib.lib()
+    pdist.init_comm()
+    stream = torch.cuda.current_stream()
+    _lib.check(L.propack_b200_set_stream(C.c_void_p(stream.cuda_stream)), "set_stream")
+
+    A, u0, k, kmax, tol = make_matrix(args.workload)     # every rank builds the same seeded matrix, keeps its shard
+    m, n = A.shape
+    lanmax = min(m + 1, n + 1, kmax)
+    op = pdist.ShardedOperator(A, rank, world)
+    sv = pdist.Solver(op, lanmax + 1, lanmax)
+
+    def barrier():
+        dist.barrier(); torch.cuda.synchronize()
+
+    # device-resident arm: Ritz vectors are formed on the device (jobu=jobv='y' inside the library) but not copied out
+    def solve_resident():
+        sv.set_start(u0)
+        propack_b200.reset_counters()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record(stream)
+        sigma, kc, info = session_solve(L, sv.id, args.workload, k, kmax, tol)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1), propack_b200.counters(), sigma, kc, info
+
+    for _ in range(args.warmup):
+        solve_resident()
+    clocks = ClockSampler(local)
+    barrier()
+    clocks.start()
+    times, steps, launches, last = [], 0, 0, None
+    for _ in range(args.steps):
+        ms, ctr, sigma, kc, info = solve_resident()
+        times.append(ms); steps += ctr["nsteps"]; launches += ctr["launches"]; last = (ctr, sigma, kc, info)
+    barrier()
+    clk = clocks.stop()
+    t = torch.tensor([float(np.sum(times))], device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t.item())
+    value = steps / (total_ms * 1e-3)          # every rank executes the same Lanczos steps: count them once
+
+    # e2e: this rank's shard from pinned host memory -> device, solve, its slices of U, V and sigma back to the host
+    rows, colt = pdist.shard_csr(A, world, rank)
+    pin = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a, dtype=dt)).pin_memory().numpy()
+    harr = (pin(rows.indptr, np.int32), pin(rows.indices, np.int32), pin(rows.data, np.float64),
+            pin(colt.indptr, np.int32), pin(colt.indices, np.int32), pin(colt.data, np.float64))
+    sv.close(); op.close()
+    e2e_t, e2e_steps = [], 0
+    for i in range(1 + max(1, min(args.steps, 3))):
+        barrier()
+        t0 = time.perf_counter()
+        h = _lib.check(L.propack_b200_csr_create_sharded_d(C.c_int(m), C.c_int(n), *[a.ctypes.data_as(C.c_void_p) for a in harr], C.c_int(0)),
+                       "csr_create_sharded")
+        op2 = pdist.ShardedOperator.__new__(pdist.ShardedOperator)
+        op2.handle, op2.dtype, op2.pfx, op2.shape, op2.rank, op2.world = h, np.dtype(np.float64), "d", (m, n), rank, world
+        op2.rows, op2.cols = pdist.shard_bounds(m, world, rank), pdist.shard_bounds(n, world, rank)
+        sv2 = pdist.Solver(op2, lanmax + 1, lanmax)
+        sv2.set_start(u0)
+        propack_b200.reset_counters()
+        if args.workload in IRL_P:
+            r = sv2.lansvd_irl("L", kmax, IRL_P[args.workload], k, IRL_MAXITER, tol=tol, cgs=True)
+        else:
+            r = sv2.lansvd(k, kmax, tol=tol, cgs=True)
+        torch.cuda.synchronize()
+        barrier()
+        dt = time.perf_counter() - t0
+        if i >= 1:
+            e2e_t.append(dt); e2e_steps += propack_b200.counters()["nsteps"]
+        sv2.close(); op2.close()
+    te = torch.tensor([float(np.sum(e2e_t))], device="cuda"); dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_val = e2e_steps / float(te.item())
+    h2d = sum(a.nbytes for a in harr) + (op2.rows[1] - op2.rows[0]) * 8
+    d2h = ((op2.rows[1] - op2.rows[0]) + (op2.cols[1] - op2.cols[0])) * k * 8 + 2 * k * 8
+    nar, nag, agb = C.c_longlong(0), C.c_longlong(0), C.c_double(0)
+    L.propack_b200_comm_stats(C.byref(nar), C.byref(nag), C.byref(agb))
+    if rank == 0:
+        ctr, sigma, kc, info = last
+        peak, peak_src = peaks()
+        line = {
+            "metric": "lanczos_steps_per_s", "value": value, "unit": "steps/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": dict(config_dict(args.workload, A, k, kmax, tol),
+                           parallelism=f"rows of A and U, and V-vectors, block-sharded over {world} GPUs; NCCL all-gather of the "
+                                       f"SpMV input, all-reduce of reorthogonalisation coefficients and norm partials"),
+            "time_to_k_triplets_s": total_ms / args.steps / 1e3, "lanczos_steps_per_solve": ctr["nsteps"], "converged": kc,
+            "info": info, "sigma_1": float(sigma[0]) if kc else None, "sigma_k": float(sigma[-1]) if kc else None,
+            "gpu_launches": int(launches), "host_syncs_per_solve": ctr["host_syncs"],
+            "collectives_total": {"allreduce": nar.value, "allgather": nag.value, "allgather_gbytes": agb.value / 1e9},
+            "e2e": {"value": e2e_val, "unit": "steps/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "time_to_k_triplets_s": float(np.mean(e2e_t)),
+                    "path": "per rank: propack_b200_csr_create_sharded_d (pinned host shard) + solver session + local U,V slices and "
+                            "sigma copied back; bytes are per rank"},
+            "roofline": None, "clocks": clk,
+        }
+        print(json.dumps(line))
+    pdist.finalize_comm()
+    dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -338,6 +492,8 @@ def main():
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        run_ours_sharded(args)
     else:
         run_ours(args)
 

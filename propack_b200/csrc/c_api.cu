@@ -70,24 +70,6 @@ bool is_yes(const char* c) { return c && (*c == 'y' || *c == 'Y'); }
 // ---------------------------------------------------------------------------------------------------
 // CSR registration: upload, device-independent host analysis of row lengths, transpose.
 // ---------------------------------------------------------------------------------------------------
-// Stable counting-sort transpose on the host: CSR(A) -> CSR(A^T) with sorted row indices inside each
-// column -- the unique canonical form, identical to scipy's tocsc() / (A.T).tocsr() with sorted indices.
-template <class T>
-void transpose_csr(int m, int n, const int* rp, const int* ci, const T* va, std::vector<int>& trp, std::vector<int>& tci,
-                   std::vector<T>& tva) {
-  const long nnz = rp[m];
-  trp.assign((size_t)n + 1, 0);
-  tci.resize(nnz); tva.resize(nnz);
-  for (long p = 0; p < nnz; ++p) trp[ci[p] + 1] += 1;
-  for (int j = 0; j < n; ++j) trp[j + 1] += trp[j];
-  std::vector<int> next(trp.begin(), trp.end() - 1);
-  for (int i = 0; i < m; ++i)
-    for (int p = rp[i]; p < rp[i + 1]; ++p) {
-      const int q = next[ci[p]]++;
-      tci[q] = i; tva[q] = va[p];
-    }
-}
-
 template <class T> void fill_device_csr(CsrDevice<T>& D, int rows, int cols, long nnz, const DeviceBuffer<int>& rp,
                                         const DeviceBuffer<int>& ci, const DeviceBuffer<T>& va) {
   D.rows = rows; D.cols = cols; D.nnz = nnz; D.rp = rp.p; D.ci = ci.p; D.va = va.p;
@@ -97,36 +79,27 @@ template <class T> void fill_device_csr(CsrDevice<T>& D, int rows, int cols, lon
 
 template <class T> int csr_create(int m, int n, const int* rowptr, const int* colind, const void* values_, int base) {
   PB_API_TRY
-  Context::get();
+  Context& c = Context::get();
   const T* values = static_cast<const T*>(values_);
   if (m <= 0 || n <= 0 || !rowptr || !colind || !values) throw std::runtime_error("propack_b200: bad CSR arguments");
   const long nnz = (long)rowptr[m] - base;
-  std::vector<int> rp(m + 1), ci(nnz);
-  for (int i = 0; i <= m; ++i) rp[i] = rowptr[i] - base;
-  for (long p = 0; p < nnz; ++p) {
-    ci[p] = colind[p] - base;
-    if (ci[p] < 0 || ci[p] >= n) throw std::runtime_error("propack_b200: CSR column index out of range");
-  }
-  // canonical form: sort indices inside each row if needed (stable w.r.t. values)
-  for (int i = 0; i < m; ++i) {
-    bool sorted = true;
-    for (int p = rp[i] + 1; p < rp[i + 1]; ++p) if (ci[p - 1] > ci[p]) { sorted = false; break; }
-    if (!sorted) throw std::runtime_error("propack_b200: CSR column indices must be sorted within each row");
-  }
+  if (rowptr[0] != base || nnz < 0) throw std::runtime_error("propack_b200: CSR row pointers do not start at the index base");
   auto op = std::make_shared<CsrOperator<T>>();
   op->m = m; op->n = n;
-  std::vector<int> trp, tci; std::vector<T> tva;
-  transpose_csr<T>(m, n, rp.data(), ci.data(), values, trp, tci, tva);
   op->rp.alloc(m + 1); op->ci.alloc(std::max<long>(nnz, 1)); op->va.alloc(std::max<long>(nnz, 1));
   op->trp.alloc(n + 1); op->tci.alloc(std::max<long>(nnz, 1)); op->tva.alloc(std::max<long>(nnz, 1));
-  PB_CUDA(cudaMemcpy(op->rp.p, rp.data(), sizeof(int) * (m + 1), cudaMemcpyHostToDevice));
-  PB_CUDA(cudaMemcpy(op->trp.p, trp.data(), sizeof(int) * (n + 1), cudaMemcpyHostToDevice));
+  // the three host arrays go up as they are; re-basing, validation (column range, sorted rows) and the canonical
+  // transpose run on the device (csr_build.cu)
+  PB_CUDA(cudaMemcpyAsync(op->rp.p, rowptr, sizeof(int) * (m + 1), cudaMemcpyHostToDevice, c.stream));
   if (nnz) {
-    PB_CUDA(cudaMemcpy(op->ci.p, ci.data(), sizeof(int) * nnz, cudaMemcpyHostToDevice));
-    PB_CUDA(cudaMemcpy(op->va.p, values, sizeof(T) * nnz, cudaMemcpyHostToDevice));
-    PB_CUDA(cudaMemcpy(op->tci.p, tci.data(), sizeof(int) * nnz, cudaMemcpyHostToDevice));
-    PB_CUDA(cudaMemcpy(op->tva.p, tva.data(), sizeof(T) * nnz, cudaMemcpyHostToDevice));
+    PB_CUDA(cudaMemcpyAsync(op->ci.p, colind, sizeof(int) * nnz, cudaMemcpyHostToDevice, c.stream));
+    PB_CUDA(cudaMemcpyAsync(op->va.p, values, sizeof(T) * nnz, cudaMemcpyHostToDevice, c.stream));
   }
+  k_rebase(c, m + 1, op->rp.p, base);
+  k_rebase(c, nnz, op->ci.p, base);
+  const int st = k_csr_transpose<T>(c, m, n, nnz, op->rp.p, op->ci.p, op->va.p, op->trp.p, op->tci.p, op->tva.p);
+  if (st & 2) throw std::runtime_error("propack_b200: CSR column index out of range");
+  if (st & 1) throw std::runtime_error("propack_b200: CSR column indices must be sorted within each row");
   fill_device_csr<T>(op->A, m, n, nnz, op->rp, op->ci, op->va);
   fill_device_csr<T>(op->At, n, m, nnz, op->trp, op->tci, op->tva);
   OpEntry e; e.tag = abi<T>::tag; e.kind = 0; e.op = op;

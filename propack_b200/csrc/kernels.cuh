@@ -55,6 +55,12 @@ int csr_lanes_per_row_log2(long nnz, int rows, int nb);
 template <class T>
 void k_spmv(Context& c, const CsrDevice<T>& A, bool conj, const T* x, T* y, real_t<T> coef, const T* prev, Pending* nrm);
 
+// --- operator registration (setup): device-side transpose + validation, csr_build.cu ---------------------------
+// CSR(A) -> canonical CSR(A^T) (all device pointers).  Returns 0 / 1 (unsorted row) / 2 (index out of range).
+template <class T>
+int k_csr_transpose(Context& c, int rows, int cols, long nnz, const int* rp, const int* ci, const T* va, int* trp, int* tci, T* tva);
+void k_rebase(Context& c, long n, int* a, int base);  // a[i] -= base (Fortran 1-based index arrays)
+
 // --- tall in-place GEMM (reference: dgemm_ovwr_left, double/dgemm_ovwr.F:56-87) --------------------
 // A(:,0:N) <- A(:,0:K) * W,  W real K x N column-major (ld = K) in HOST memory (it comes from the host
 // bidiagonal SVD); it is packed into DMMA fragment order and uploaded by the wrapper.

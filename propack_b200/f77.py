@@ -117,16 +117,29 @@ def _options(pfx, delta, eta, anorm, min_relgap=None):
     return np.array(v, dtype=R)
 
 
+def _basis_buffers(op, m, n, ucols, vcols, k, U, V, u0):
+    """The caller-owned U, V of the Fortran interface.  The reference needs (m, kmax+1) / (n, kmax); this library keeps the
+    Krylov bases in HBM and only reads U(:,1) and writes the first k columns, so caller-provided (e.g. pinned) buffers
+    with >= max(k,1) columns are accepted too."""
+    if U is None:
+        U = np.zeros((m, ucols), dtype=op.dtype, order="F")
+    if V is None:
+        V = np.zeros((n, vcols), dtype=op.dtype, order="F")
+    for name, a, rows in (("U", U, m), ("V", V, n)):
+        if a.dtype != op.dtype or not a.flags.f_contiguous or a.shape[0] != rows or a.shape[1] < max(k, 1):
+            raise ValueError(f"{name} must be Fortran-ordered {op.dtype} with {rows} rows and >= {max(k, 1)} columns")
+    if u0 is not None:
+        U[:, 0] = u0
+    return U, V
+
+
 def lansvd(op: Operator, k, kmax, tol=0.0, u0=None, delta=None, eta=None, anorm=0.0, cgs=False, elr=True,
-           jobu=True, jobv=True):
+           jobu=True, jobv=True, U=None, V=None):
     """xLANSVD through the Fortran ABI (reference double/dlansvd.F:1-3).  Host arrays in and out."""
     pfx, R = op.pfx, REAL[op.pfx]
     m, n = op.shape
     kmax = min(m + 1, n + 1, kmax)
-    U = np.zeros((m, kmax + 1), dtype=op.dtype, order="F")
-    V = np.zeros((n, kmax), dtype=op.dtype, order="F")
-    if u0 is not None:
-        U[:, 0] = u0
+    U, V = _basis_buffers(op, m, n, kmax + 1, kmax, k, U, V, u0)
     sigma = np.zeros(max(k, 1), dtype=R)
     bnd = np.zeros(max(k, 1), dtype=R)
     doption = _options(pfx, delta, eta, anorm)
@@ -149,17 +162,14 @@ def lansvd(op: Operator, k, kmax, tol=0.0, u0=None, delta=None, eta=None, anorm=
 
 
 def lansvd_irl(op: Operator, k, dim, p=None, which="L", maxiter=1000, tol=0.0, u0=None, delta=None, eta=None,
-               anorm=0.0, cgs=False, elr=True, min_relgap=0.002, jobu=True, jobv=True):
+               anorm=0.0, cgs=False, elr=True, min_relgap=0.002, jobu=True, jobv=True, U=None, V=None):
     """xLANSVD_IRL through the Fortran ABI (reference double/dlansvd_irl.F:1-3)."""
     pfx, R = op.pfx, REAL[op.pfx]
     m, n = op.shape
     dim = min(m + 1, n + 1, dim)
     if p is None:
         p = dim - k
-    U = np.zeros((m, dim + 1), dtype=op.dtype, order="F")
-    V = np.zeros((n, dim), dtype=op.dtype, order="F")
-    if u0 is not None:
-        U[:, 0] = u0
+    U, V = _basis_buffers(op, m, n, dim + 1, dim, k, U, V, u0)
     sigma = np.zeros(dim + 1, dtype=R)
     bnd = np.zeros(dim + 1, dtype=R)
     doption = _options(pfx, delta, eta, anorm, min_relgap)
