@@ -43,6 +43,9 @@ WORKLOADS = {
     "c5": (10_000_000, 10_000_000, None, 100, 300, 1e-10),
     "c5-small": (1_000_000, 1_000_000, None, 100, 300, 1e-10),
 }
+WORKLOADS["c4"] = (2_000_000, 2_000_000, "powerlaw", 64, 700, 1e-10)        # BASELINE configs[3]: complex16, ZLANSVD
+WORKLOADS["c4-small"] = (200_000, 200_000, "powerlaw", 32, 400, 1e-10)
+COMPLEX = {"c4", "c4-small"}
 IRL_P = {"c5": 200, "c5-small": 200}   # workloads solved with DLANSVD_IRL: shifts per restart (kmax column = dim)
 IRL_MAXITER = 50
 CPU_SAMPLE_STEPS = 150  # Lanczos steps of the same problem the CPU baseline runs per sample
@@ -52,7 +55,16 @@ def make_matrix(name):
     import scipy.sparse as sp
     m, n, dens, k, kmax, tol = WORKLOADS[name]
     rng = np.random.default_rng(0)
-    if dens is None:   # exactly 10 uniform columns per row (the rare duplicates inside a row are summed)
+    if dens == "powerlaw":   # row lengths min(1 + floor(Zipf(2)), 10000), renormalised to ~10 per row, complex values
+        lens = np.minimum(rng.zipf(2.0, size=m), 10_000).astype(np.float64)
+        lens = np.maximum(1, np.rint(lens * (10.0 * m / lens.sum()))).astype(np.int64)
+        lens = np.minimum(lens, n)
+        rows = np.repeat(np.arange(m, dtype=np.int32), lens)
+        cols = rng.integers(0, n, size=rows.size, dtype=np.int32)
+        vals = rng.standard_normal(rows.size) + 1j * rng.standard_normal(rows.size)
+        A = sp.csr_array(sp.coo_array((vals, (rows, cols)), shape=(m, n)))   # duplicates inside a row are summed
+        A.sum_duplicates()
+    elif dens is None:   # exactly 10 uniform columns per row (the rare duplicates inside a row are summed)
         per = 10
         cols = rng.integers(0, n, size=(m, per), dtype=np.int32)
         cols.sort(axis=1)
@@ -62,7 +74,7 @@ def make_matrix(name):
     else:
         A = sp.random_array((m, n), density=dens, format="csr", rng=rng, data_sampler=rng.standard_normal)
     A.sort_indices()
-    u0 = np.random.default_rng(1).uniform(size=m)
+    u0 = np.random.default_rng(1).uniform(size=m).astype(A.dtype)
     return A, u0, k, kmax, tol
 
 
@@ -121,6 +133,10 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def wl_dtype(name):
+    return ("c128", 16) if name in COMPLEX else ("f64", 8)
+
+
 def reorth_bytes(ctr, w=8):
     """one Gram-Schmidt pass of a length-L vector against l columns moves w*L*(2l+3) bytes."""
     return w * (2 * ctr["reorth_elems"] + 3 * ctr["reorth_vec_elems"])
@@ -133,9 +149,10 @@ def cpu_sample(A, u0, steps):
     """Time `steps` Lanczos steps (DLANBPRO, k0=0) of the same problem on the host cores. Returns (steps/s, seconds)."""
     from oracle import oracle_py as O
     L = O.lib()
-    op = O.Operator(A, np.float64)
+    dt_ = np.dtype(A.dtype)
+    op = O.Operator(A, dt_)
     m, n = A.shape
-    U = np.zeros((m, steps + 1), order="F"); V = np.zeros((n, steps), order="F")
+    U = np.zeros((m, steps + 1), dtype=dt_, order="F"); V = np.zeros((n, steps), dtype=dt_, order="F")
     U[:, 0] = u0
     B = np.zeros((steps, 2), order="F")
     eps = np.finfo(np.float64).eps
@@ -144,7 +161,7 @@ def cpu_sample(A, u0, steps):
     kk, rn, ierr = C.c_int(steps), C.c_double(float(np.linalg.norm(u0))), C.c_int(0)
     O.stats_reset()
     t0 = time.perf_counter()
-    L.oracle_lanbpro_d(C.c_int(m), C.c_int(n), C.c_int(0), C.byref(kk), *op.args(), U.ctypes.data_as(C.c_void_p), C.c_long(m),
+    getattr(L, "oracle_lanbpro_z" if dt_.kind == "c" else "oracle_lanbpro_d")(C.c_int(m), C.c_int(n), C.c_int(0), C.byref(kk), *op.args(), U.ctypes.data_as(C.c_void_p), C.c_long(m),
                        V.ctypes.data_as(C.c_void_p), C.c_long(n), B.ctypes.data_as(C.c_void_p), C.c_int(steps), C.byref(rn),
                        doption.ctypes.data_as(C.c_void_p), ioption.ctypes.data_as(C.c_void_p), C.byref(ierr))
     dt = time.perf_counter() - t0
@@ -167,7 +184,7 @@ def run_reference(args):
     line = {
         "impl": "reference", "metric": "lanczos_steps_per_s", "value": value, "unit": "steps/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * float(np.mean(secs)), "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "scaling": "weak", "vs_baseline": None, "dtype": wl_dtype(args.workload)[0], "data": "synthetic",
         "config": config_dict(args.workload, A, k, kmax, tol),
         "cpu_baseline": {"value": value, "unit": "steps/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -177,11 +194,13 @@ def run_reference(args):
 
 def config_dict(name, A, k, kmax, tol):
     irl = name in IRL_P
-    which = "configs[4]" if irl else "configs[1]"
-    drv = f"DLANSVD_IRL double dim={kmax} p={IRL_P[name]}" if irl else f"kmax={kmax}, DLANSVD double"
-    return {"workload": f"BASELINE {which} '{name}': synthetic random CSR {A.shape[0]}x{A.shape[1]}, nnz={A.nnz} "
-                        f"(~{A.nnz / A.shape[0]:.1f}/row), k={k}, {drv}, tol={tol:g}, CGS, ELR",
-            "driver": "dlansvd_irl" if irl else "dlansvd", "k": k, "kmax": kmax, "tol": tol, "nnz": int(A.nnz),
+    cz = name in COMPLEX
+    which = "configs[4]" if irl else ("configs[3]" if cz else "configs[1]")
+    drv = f"DLANSVD_IRL double dim={kmax} p={IRL_P[name]}" if irl else (f"kmax={kmax}, ZLANSVD complex16" if cz else f"kmax={kmax}, DLANSVD double")
+    kind = "power-law-row complex CSR" if cz else "random CSR"
+    return {"workload": f"BASELINE {which} '{name}': synthetic {kind} {A.shape[0]}x{A.shape[1]}, nnz={A.nnz} "
+                        f"(~{A.nnz / A.shape[0]:.1f}/row, longest row {int(np.diff(A.indptr).max())}), k={k}, {drv}, tol={tol:g}, CGS, ELR",
+            "driver": ("zlansvd" if cz else "dlansvd_irl" if irl else "dlansvd"), "k": k, "kmax": kmax, "tol": tol, "nnz": int(A.nnz),
             "rows": int(A.shape[0]), "cols": int(A.shape[1]), "l2_policy": "inputs larger than L2 (no flush needed)"}
 
 
@@ -274,40 +293,44 @@ def run_ours(args):
     ph = propack_b200.phase_ms()
     propack_b200.set_profile(False)
     peak, peak_src = peaks()
-    rb = reorth_bytes(pctr)
+    dts, w = wl_dtype(args.workload)
+    rb = reorth_bytes(pctr, w)
     reorth_ms = ph["reorth"]["ms"]
     achieved = rb / (reorth_ms * 1e-3) / 1e9 if reorth_ms > 0 else 0.0
-    spmv_bytes = (pctr["nopx"] / 2.0) * (op.bytes_per_product(False) + op.bytes_per_product(True) + 8.0 * (m + n))
+    spmv_bytes = (pctr["nopx"] / 2.0) * (op.bytes_per_product(False) + op.bytes_per_product(True) + float(w) * (m + n))
     spmv_gbs = spmv_bytes / (ph["aprod"]["ms"] * 1e-3) / 1e9 if ph["aprod"]["ms"] > 0 else 0.0
     # isolated kernels (device-resident synthetic operands, L2 flushed between launches)
     L.propack_b200_bench_reorth_d.argtypes = [C.c_long, C.c_int, C.c_int, C.c_int]
     iso = {}
-    for l in (64, 256):
+    for l in (64, 256):   # (f64 micro-benchmark of the GEMV pair; the complex kernels stream the same bytes per element pair)
         t_ms = L.propack_b200_bench_reorth_d(m, l, 5, 1)
-        iso[f"reorth_L{m}_l{l}_gbs"] = 8.0 * m * (2 * l + 3) / (t_ms * 1e-3) / 1e9
+        iso[f"reorth_f64_L{m}_l{l}_gbs"] = 8.0 * m * (2 * l + 3) / (t_ms * 1e-3) / 1e9
     for adj in (0, 1):
         t_ms = L.propack_b200_bench_spmv(C.c_int(op.handle), C.c_int(adj), C.c_int(10), C.c_int(1))
-        iso[f"spmv_{'t' if adj else 'n'}_gbs"] = (op.bytes_per_product(bool(adj)) + 8.0 * (n if adj else m)) / (t_ms * 1e-3) / 1e9
+        iso[f"spmv_{'t' if adj else 'n'}_gbs"] = (op.bytes_per_product(bool(adj)) + float(w) * (n if adj else m)) / (t_ms * 1e-3) / 1e9
 
     # ---- e2e: Fortran-ABI dlansvd_ with host buffers (matrix upload, start vector up, U/V/sigma down) --------
     rp = np.ascontiguousarray(A.indptr, dtype=np.int32); ci = np.ascontiguousarray(A.indices, dtype=np.int32)
     va = np.ascontiguousarray(A.data)
+    pfx = "z" if args.workload in COMPLEX else "d"
+    tdt = torch.complex128 if pfx == "z" else torch.float64
     pin = lambda a: torch.from_numpy(a).pin_memory().numpy()
     rp, ci, va, u0p = pin(rp), pin(ci), pin(va), pin(u0)
     # caller-owned result buffers of the Fortran interface, in pinned memory (allocated once, outside the timed region)
-    Upin = torch.empty((k + 1, m), dtype=torch.float64).pin_memory().numpy().T
-    Vpin = torch.empty((k + 1, n), dtype=torch.float64).pin_memory().numpy().T
+    Upin = torch.empty((k + 1, m), dtype=tdt).pin_memory().numpy().T
+    Vpin = torch.empty((k + 1, n), dtype=tdt).pin_memory().numpy().T
 
     e2e_create = []
 
     def solve_e2e():
         t0 = time.perf_counter()
         op2 = f77.Operator.__new__(f77.Operator)
-        h = _lib.check(L.propack_b200_csr_create_d(C.c_int(m), C.c_int(n), rp.ctypes.data_as(C.c_void_p), ci.ctypes.data_as(C.c_void_p),
-                                                    va.ctypes.data_as(C.c_void_p), C.c_int(0)), "csr_create")
+        h = _lib.check(getattr(L, f"propack_b200_csr_create_{pfx}")(C.c_int(m), C.c_int(n), rp.ctypes.data_as(C.c_void_p),
+                                                                    ci.ctypes.data_as(C.c_void_p), va.ctypes.data_as(C.c_void_p), C.c_int(0)),
+                       "csr_create")
         e2e_create.append(time.perf_counter() - t0)
-        op2.handle, op2._cb, op2.dtype, op2.pfx, op2.shape = h, None, np.dtype(np.float64), "d", (m, n)
-        op2.iparm = np.array([h, 0], dtype=np.int32); op2.parm = np.zeros(2)
+        op2.handle, op2._cb, op2.dtype, op2.pfx, op2.shape = h, None, np.dtype(A.dtype), pfx, (m, n)
+        op2.iparm = np.array([h, 0], dtype=np.int32); op2.parm = np.zeros(2, dtype=A.dtype)
         if args.workload in IRL_P:
             r = f77.lansvd_irl(op2, k, kmax, p=IRL_P[args.workload], maxiter=IRL_MAXITER, tol=tol, u0=u0p, cgs=True, U=Upin, V=Vpin)
         else:
@@ -330,7 +353,7 @@ def run_ours(args):
         s = torch.tensor([float(e2e_steps)], device="cuda"); dist.all_reduce(s)
         e2e_val = float(s.item()) / float(t.item())
     h2d = rp.nbytes + ci.nbytes + va.nbytes + u0.nbytes
-    d2h = (m + n) * k * 8 + 2 * k * 8
+    d2h = (m + n) * k * w + 2 * k * 8
 
     # ---- cpu baseline (rank 0, N=1 only): bounded sample of the same workload on the host cores --------------
     cpu = None
@@ -345,7 +368,7 @@ def run_ours(args):
         line = {
             "metric": "lanczos_steps_per_s", "value": value, "unit": "steps/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "scaling": "weak", "vs_baseline": None, "dtype": dts, "data": "synthetic",
             "config": dict(config_dict(args.workload, A, k, kmax, tol),
                            parallelism=("single GPU" if world == 1 else f"{world} independent replicas (row-sharded path not in this round)")),
             "time_to_k_triplets_s": total_ms / args.steps / 1e3, "lanczos_steps_per_solve": ctr["nsteps"],
@@ -377,6 +400,10 @@ def run_ours_sharded(args):
     import torch
     import torch.distributed as dist
     world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    # NCCL / torchrun banners must not land on stdout (rank 0 prints exactly one JSON line): fd 1 -> fd 2 until the end
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     import propack_b200
@@ -462,7 +489,7 @@ def run_ours_sharded(args):
         line = {
             "metric": "lanczos_steps_per_s", "value": value, "unit": "steps/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong",
-            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "vs_baseline": None, "dtype": wl_dtype(args.workload)[0], "data": "synthetic",
             "config": dict(config_dict(args.workload, A, k, kmax, tol),
                            parallelism=f"rows of A and U, and V-vectors, block-sharded over {world} GPUs; NCCL all-gather of the "
                                        f"SpMV input, all-reduce of reorthogonalisation coefficients and norm partials"),
@@ -476,7 +503,10 @@ def run_ours_sharded(args):
                             "sigma copied back; bytes are per rank"},
             "roofline": None, "clocks": clk,
         }
-        print(json.dumps(line))
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
+        print(json.dumps(line), flush=True)
+        os.dup2(2, 1)
     pdist.finalize_comm()
     dist.destroy_process_group()
 
