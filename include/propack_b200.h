@@ -196,6 +196,10 @@ int propack_b200_dense_create_d(int m, int n, const double* A, long lda);
 int propack_b200_dense_create_c(int m, int n, const pb200_complex8* A, long lda);
 int propack_b200_dense_create_z(int m, int n, const pb200_complex16* A, long lda);
 int propack_b200_dense_adopt_device_d(int m, int n, const double* A_device, long lda);
+/* synthetic dense operator generated on the device (BASELINE config 3: 2M x 4096 = 65.5 GB never exists on the host):
+ * A(i,j) = u(i,j) + sum_g table[g][byte_g(X(i)^Y(j))], see csrc/dense_gen.cu and propack_b200/synth.py (bit-identical
+ * numpy replica for parity tests).  Plays the role of the user's APROD data (double/dlansvd.F:20-33). */
+int propack_b200_dense_create_synthetic_d(int m, int n, unsigned long long seed, const double* table16x256);
 int propack_b200_op_destroy(int handle);
 /* HBM bytes one product moves by the SURVEY 8(d) model (adjoint = 0: A x, 1: A^H x) */
 double propack_b200_op_bytes(int handle, int adjoint);

@@ -70,9 +70,26 @@ bool is_yes(const char* c) { return c && (*c == 'y' || *c == 'Y'); }
 // ---------------------------------------------------------------------------------------------------
 // CSR registration: upload, device-independent host analysis of row lengths, transpose.
 // ---------------------------------------------------------------------------------------------------
+// rp_host: the row pointers on the host (0-based), or null to fetch them from the device (the transpose's are
+// produced there); used once to list the long rows.
 template <class T> void fill_device_csr(CsrDevice<T>& D, int rows, int cols, long nnz, const DeviceBuffer<int>& rp,
-                                        const DeviceBuffer<int>& ci, const DeviceBuffer<T>& va) {
+                                        const DeviceBuffer<int>& ci, const DeviceBuffer<T>& va, const int* rp_host, int rp_base,
+                                        DeviceBuffer<int>& long_rows) {
   D.rows = rows; D.cols = cols; D.nnz = nnz; D.rp = rp.p; D.ci = ci.p; D.va = va.p;
+  std::vector<int> tmp;
+  if (!rp_host) {
+    tmp.resize((size_t)rows + 1);
+    PB_CUDA(cudaMemcpy(tmp.data(), rp.p, sizeof(int) * ((size_t)rows + 1), cudaMemcpyDeviceToHost));
+    rp_host = tmp.data(); rp_base = 0;
+  }
+  (void)rp_base;  // differences of row pointers do not depend on the index base
+  const std::vector<int> lr = csr_long_rows(rp_host, rows, spmv_group_nnz<T>());
+  D.n_long = (int)lr.size();
+  if (D.n_long) {
+    long_rows.alloc(lr.size());
+    PB_CUDA(cudaMemcpy(long_rows.p, lr.data(), sizeof(int) * lr.size(), cudaMemcpyHostToDevice));
+    D.long_rows = long_rows.p;
+  }
   D.lpr_log2 = csr_lanes_per_row_log2(nnz, rows, spmv_group_nnz<T>());
   if (const char* e = std::getenv("PROPACK_B200_SPMV_LPR_LOG2")) D.lpr_log2 = std::min(5, std::max(0, std::atoi(e)));
 }
@@ -100,8 +117,8 @@ template <class T> int csr_create(int m, int n, const int* rowptr, const int* co
   const int st = k_csr_transpose<T>(c, m, n, nnz, op->rp.p, op->ci.p, op->va.p, op->trp.p, op->tci.p, op->tva.p);
   if (st & 2) throw std::runtime_error("propack_b200: CSR column index out of range");
   if (st & 1) throw std::runtime_error("propack_b200: CSR column indices must be sorted within each row");
-  fill_device_csr<T>(op->A, m, n, nnz, op->rp, op->ci, op->va);
-  fill_device_csr<T>(op->At, n, m, nnz, op->trp, op->tci, op->tva);
+  fill_device_csr<T>(op->A, m, n, nnz, op->rp, op->ci, op->va, rowptr, base, op->lrows);
+  fill_device_csr<T>(op->At, n, m, nnz, op->trp, op->tci, op->tva, nullptr, 0, op->tlrows);
   OpEntry e; e.tag = abi<T>::tag; e.kind = 0; e.op = op;
   const int h = g_next_op++;
   g_ops[h] = e;
@@ -130,7 +147,7 @@ int csr_create_sharded(int mg, int ng, const int* row_rp, const int* row_ci, con
   op->ld_m = shard_slice(mg, cm.world); op->ld_n = shard_slice(ng, cm.world);
   op->sharded = true;
   auto upload = [&](int rows, long width, const int* rp_in, const int* ci_in, const T* va_in, DeviceBuffer<int>& rp, DeviceBuffer<int>& ci,
-                    DeviceBuffer<T>& va, CsrDevice<T>& D, long cols_padded) {
+                    DeviceBuffer<T>& va, CsrDevice<T>& D, long cols_padded, DeviceBuffer<int>& lr) {
     std::vector<int> hrp(rows + 1);
     for (int i = 0; i <= rows; ++i) hrp[i] = rp_in[i] - base;
     if (hrp[0] != 0) throw std::runtime_error("propack_b200: sharded CSR row pointers must start at the index base");
@@ -149,10 +166,10 @@ int csr_create_sharded(int mg, int ng, const int* row_rp, const int* row_ci, con
       PB_CUDA(cudaMemcpy(ci.p, hci.data(), sizeof(int) * nnz, cudaMemcpyHostToDevice));
       PB_CUDA(cudaMemcpy(va.p, va_in, sizeof(T) * nnz, cudaMemcpyHostToDevice));
     }
-    fill_device_csr<T>(D, rows, (int)cols_padded, nnz, rp, ci, va);
+    fill_device_csr<T>(D, rows, (int)cols_padded, nnz, rp, ci, va, hrp.data(), 0, lr);
   };
-  upload(ml, ng, row_rp, row_ci, row_va, op->rp, op->ci, op->va, op->A, op->ld_n * cm.world);
-  upload(nl, mg, colt_rp, colt_ci, colt_va, op->trp, op->tci, op->tva, op->At, op->ld_m * cm.world);
+  upload(ml, ng, row_rp, row_ci, row_va, op->rp, op->ci, op->va, op->A, op->ld_n * cm.world, op->lrows);
+  upload(nl, mg, colt_rp, colt_ci, colt_va, op->trp, op->tci, op->tva, op->At, op->ld_m * cm.world, op->tlrows);
   op->xfull_n.alloc((size_t)op->ld_n * cm.world);
   op->xfull_m.alloc((size_t)op->ld_m * cm.world);
   PB_CUDA(cudaMemset(op->xfull_n.p, 0, sizeof(T) * op->xfull_n.n));
@@ -583,6 +600,23 @@ void printstat_(void) {  // layout follows double/printstat.F:35-75
 // ---- operators ------------------------------------------------------------------------------------------
 int propack_b200_dense_adopt_device_d(int m, int n, const double* A_device, long lda) {
   return dense_create<double>(m, n, A_device, lda, true);
+}
+int propack_b200_dense_create_synthetic_d(int m, int n, unsigned long long seed, const double* table16x256) {
+  PB_API_TRY
+  Context& c = Context::get();
+  if (m <= 0 || n <= 0 || !table16x256) throw std::runtime_error("propack_b200: bad synthetic dense arguments");
+  auto op = std::make_shared<DenseOperator<double>>();
+  op->m = m; op->n = n;
+  const long ld = Engine<double>::pad_ld(m);
+  op->store.alloc((size_t)ld * n);
+  if (ld != m) PB_CUDA(cudaMemsetAsync(op->store.p, 0, sizeof(double) * (size_t)ld * n, c.stream));  // zero padding rows
+  k_dense_synth(c, m, n, ld, seed, table16x256, op->store.p);
+  op->A = op->store.p; op->lda = ld;
+  OpEntry e; e.tag = 'd'; e.kind = 1; e.op = op;
+  const int h = g_next_op++;
+  g_ops[h] = e;
+  return h;
+  PB_API_CATCH(return code__)
 }
 int propack_b200_op_destroy(int handle) { return g_ops.erase(handle) ? 0 : -1; }
 double propack_b200_op_bytes(int handle, int adjoint) {

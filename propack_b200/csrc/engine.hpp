@@ -52,7 +52,7 @@ template <class T> struct LinOp {
 
 template <class T> struct CsrOperator : LinOp<T> {
   using R = real_t<T>;
-  DeviceBuffer<int> rp, ci, trp, tci;
+  DeviceBuffer<int> rp, ci, trp, tci, lrows, tlrows;
   DeviceBuffer<T> va, tva;
   CsrDevice<T> A, At;  // At = CSR of A^T (values not conjugated)
   void apply(Context& c, bool adjoint, const T* x, T* y, R coef, const T* prev, Pending* nrm) override {
@@ -73,7 +73,7 @@ template <class T> struct CsrOperator : LinOp<T> {
 // gathered vector directly.
 template <class T> struct ShardedCsrOperator : LinOp<T> {
   using R = real_t<T>;
-  DeviceBuffer<int> rp, ci, trp, tci;
+  DeviceBuffer<int> rp, ci, trp, tci, lrows, tlrows;
   DeviceBuffer<T> va, tva, xfull_n, xfull_m;
   CsrDevice<T> A, At;  // A: m_loc x (world*ld_n);  At: n_loc x (world*ld_m)
   void apply(Context& c, bool adjoint, const T* x, T* y, R coef, const T* prev, Pending* nrm) override {

@@ -48,9 +48,12 @@ template <class T> struct CsrDevice {
   const int* ci = nullptr;     // [nnz], sorted within a row
   const T* va = nullptr;       // [nnz]
   int lpr_log2 = 0;            // lanes per row in the reduce phase = 1 << lpr_log2 (csr_lanes_per_row_log2)
+  const int* long_rows = nullptr;  // rows with more than spmv_group_nnz/2 non-zeros (csr_long_rows), ascending
+  int n_long = 0;
 };
 // host-side analysis: lanes per row so that a group of 32/LPR rows fits a slice of nb products
 int csr_lanes_per_row_log2(long nnz, int rows, int nb);
+std::vector<int> csr_long_rows(const int* rp, int rows, int nb);
 // y <- op(A) x + coef*prev (prev may be null) ; optionally publish ||y||_2.  conj: use conj(values).
 template <class T>
 void k_spmv(Context& c, const CsrDevice<T>& A, bool conj, const T* x, T* y, real_t<T> coef, const T* prev, Pending* nrm);
@@ -60,6 +63,9 @@ void k_spmv(Context& c, const CsrDevice<T>& A, bool conj, const T* x, T* y, real
 template <class T>
 int k_csr_transpose(Context& c, int rows, int cols, long nnz, const int* rp, const int* ci, const T* va, int* trp, int* tci, T* tva);
 void k_rebase(Context& c, long n, int* a, int base);  // a[i] -= base (Fortran 1-based index arrays)
+
+// synthetic dense operator A(i,j) = u(i,j) + planted rank-128 part, evaluated on the device (dense_gen.cu)
+void k_dense_synth(Context& c, long m, int n, long lda, unsigned long long seed, const double* table_host, double* A);
 
 // --- tall in-place GEMM (reference: dgemm_ovwr_left, double/dgemm_ovwr.F:56-87) --------------------
 // A(:,0:N) <- A(:,0:K) * W,  W real K x N column-major (ld = K) in HOST memory (it comes from the host

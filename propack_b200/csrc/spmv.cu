@@ -16,7 +16,9 @@
 //   * phase 2: LPR lanes reduce each row out of shared memory, then y = sum + coef*prev and the ||y||^2 partial;
 //   * no CTA-wide barrier anywhere in the loop: every warp runs its own load/gather/reduce pipeline, and the
 //     next group's row pointers are fetched while the current gathers are in flight;
-//   * a group holding a row too long for the slice falls back to warp-per-row sweeps from global memory.
+//   * rows of a group are packed greedily into slice-sized runs, so irregular row lengths cost extra runs, not a
+//     slow path; rows longer than half a slice (power-law matrices) are done by spmv_long_kernel, one CTA per row,
+//     ahead of the main kernel, which only folds their |y|^2 into the norm.
 // The random x gathers make this kernel L1TEX-wavefront bound, not HBM bound (one wavefront per gathered lane:
 // 10 M gathers take >= 44 us on a B200 however the rest is organised).  L1 also tracks the outstanding misses,
 // so the shared-memory footprint is capped (3 CTAs x 33 KB per SM, carve-out hint 50% = the 132 KB configuration): with the carve-out at
@@ -62,12 +64,38 @@ template <class T, bool CONJ> __device__ inline T mul_(T a, T x) {
 }
 
 constexpr int kSpmvWarps = kThreads / 32;
+constexpr int kLongThreads = 128;
+
+// Rows longer than half a slice ("long rows": power-law matrices, BASELINE config 4) get a CTA each, before the main
+// kernel: y[row] = sum + coef*prev[row].  The main kernel skips them and only folds |y[row]|^2 into its norm partial,
+// so the result is still deterministic (no atomics, fixed reduction order).
+template <class T, bool CONJ>
+__global__ void __launch_bounds__(kLongThreads)
+spmv_long_kernel(CsrDevice<T> A, const T* __restrict__ x, T* __restrict__ y, real_t<T> coef, const T* __restrict__ prev) {
+  __shared__ T red[32];
+  const int row = __ldg(A.long_rows + blockIdx.x);
+  const int s = __ldg(A.rp + row), e = __ldg(A.rp + row + 1);
+  T acc = zero_<T>();
+  for (int p = s + threadIdx.x; p < e; p += kLongThreads) {
+    const T a = ldcs_(A.va + p);
+    const T xv = ldg_(x + __ldcs(A.ci + p));
+    if (CONJ) fma_conj(acc, a, xv);
+    else fma_(acc, a, xv);
+  }
+  acc = block_sum(acc, red);
+  if (threadIdx.x == 0) {
+    if (prev != nullptr) acc = acc + coef * prev[row];
+    y[row] = acc;
+  }
+}
 
 template <class T, bool CONJ>
 __global__ void __launch_bounds__(kThreads)
 spmv_kernel(CsrDevice<T> A, const T* __restrict__ x, T* __restrict__ y, real_t<T> coef, const T* __restrict__ prev,
             ReduceWs ws, int want_norm) {
   constexpr int NB = spmv_group_nnz<T>();
+  constexpr int LONG = NB / 2;
+  constexpr unsigned FULL = 0xffffffffu;
   __shared__ T prod[kSpmvWarps][NB];
   __shared__ double red[32];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -92,57 +120,49 @@ spmv_kernel(CsrDevice<T> A, const T* __restrict__ x, T* __restrict__ y, real_t<T
     load_extent(g + gstride, sn, en);  // prefetch the next group's extents
     const long row = g * rpg + sub;
     const bool ok = row < A.rows;
-    const int p0 = __shfl_sync(0xffffffffu, s, 0), pe = __shfl_sync(0xffffffffu, e, 31);
-    const int nn = pe - p0;
+    const bool is_long = (e - s) > LONG;
     T pv = zero_<T>();
-    if (ok && prev != nullptr && lg == 0) pv = ldcs_(prev + row);
-    if (nn <= NB) {
-      // ---- phase 1: products of the group's slice into the warp's shared-memory slice -----------------
-      const int* cip = A.ci + p0;
-      const T* vap = A.va + p0;
+    if (ok && prev != nullptr && lg == 0 && !is_long) pv = ldcs_(prev + row);
+    if (is_long && lg == 0) nrm += (double)abs2_(y[row]);  // produced by spmv_long_kernel (earlier launch)
+    // Greedy packing of the group's rows into slice-sized runs [a, b): consecutive short rows whose non-zeros fit
+    // the warp's slice.  Uniform short rows give one run per group; a long row splits the group around it.
+    int a = 0;
+    while (a < rpg) {
+      const int first_long = (int)__reduce_min_sync(FULL, (unsigned)((is_long && sub >= a) ? sub : rpg));
+      if (first_long == a) { ++a; continue; }
+      const int pa = __shfl_sync(FULL, s, a << lpr_log2);
+      const bool fits = sub >= a && sub < first_long && (e - pa) <= NB;
+      const int b = (int)__reduce_max_sync(FULL, (unsigned)(fits ? sub + 1 : 0));   // >= a+1: a short row always fits
+      const int nn = __shfl_sync(FULL, e, ((b - 1) << lpr_log2)) - pa;
+      // ---- phase 1: products of the run's slice into the warp's shared-memory slice -----------------------
+      const int* cip = A.ci + pa;
+      const T* vap = A.va + pa;
       for (int i0 = 0; i0 < nn; i0 += kSpmvU * 32) {
         int c[kSpmvU];
-        T a[kSpmvU], xv[kSpmvU];
+        T av[kSpmvU], xv[kSpmvU];
 #pragma unroll
         for (int u = 0; u < kSpmvU; ++u) { const int i = i0 + u * 32 + lane; c[u] = i < nn ? __ldcs(cip + i) : -1; }
 #pragma unroll
-        for (int u = 0; u < kSpmvU; ++u) { const int i = i0 + u * 32 + lane; a[u] = i < nn ? ldcs_(vap + i) : zero_<T>(); }
+        for (int u = 0; u < kSpmvU; ++u) { const int i = i0 + u * 32 + lane; av[u] = i < nn ? ldcs_(vap + i) : zero_<T>(); }
 #pragma unroll
         for (int u = 0; u < kSpmvU; ++u) xv[u] = c[u] >= 0 ? ldg_(x + c[u]) : zero_<T>();
 #pragma unroll
-        for (int u = 0; u < kSpmvU; ++u) { const int i = i0 + u * 32 + lane; if (i < nn) pw[i] = mul_<T, CONJ>(a[u], xv[u]); }
+        for (int u = 0; u < kSpmvU; ++u) { const int i = i0 + u * 32 + lane; if (i < nn) pw[i] = mul_<T, CONJ>(av[u], xv[u]); }
       }
       __syncwarp();
-      // ---- phase 2: LPR lanes per row ----------------------------------------------------------------------
+      // ---- phase 2: LPR lanes per row ------------------------------------------------------------------------
+      const bool mine = sub >= a && sub < b;
       T acc = zero_<T>();
-      for (int q = s - p0 + lg; q < e - p0; q += lpr) acc = acc + pw[q];
+      if (mine)
+        for (int q = s - pa + lg; q < e - pa; q += lpr) acc = acc + pw[q];
       for (int o = lpr >> 1; o > 0; o >>= 1) acc = acc + shfl_down_(acc, o, lpr);
-      __syncwarp();  // the slice is rewritten by the next group
-      if (ok && lg == 0) {
+      __syncwarp();  // the slice is rewritten by the next run
+      if (mine && ok && lg == 0) {
         if (prev != nullptr) acc = acc + coef * pv;
         y[row] = acc;
         nrm += (double)abs2_(acc);
       }
-    } else {
-      // ---- a row too long for the slice is in this group: warp-per-row sweeps from global memory --------
-      for (int r = 0; r < rpg; ++r) {
-        const int rs = __shfl_sync(0xffffffffu, s, r << lpr_log2), re = __shfl_sync(0xffffffffu, e, r << lpr_log2);
-        T acc = zero_<T>();
-        for (int p = rs + lane; p < re; p += 32) {
-          const T a = ldcs_(A.va + p);
-          const T xv = ldg_(x + __ldcs(A.ci + p));
-          if (CONJ) fma_conj(acc, a, xv);
-          else fma_(acc, a, xv);
-        }
-        acc = warp_sum(acc);
-        const T pr = shfl_idx_(pv, r << lpr_log2);
-        const long rr = g * rpg + r;
-        if (lane == 0 && rr < A.rows) {
-          if (prev != nullptr) acc = acc + coef * pr;
-          y[rr] = acc;
-          nrm += (double)abs2_(acc);
-        }
-      }
+      a = b;
     }
     s = sn; e = en;
   }
@@ -168,13 +188,26 @@ void k_spmv(Context& c, const CsrDevice<T>& A, bool conj, const T* x, T* y, real
     PB_CUDA(cudaFuncSetAttribute(spmv_kernel<T, false>, cudaFuncAttributePreferredSharedMemoryCarveout, kSpmvCarveoutPct));
     attr_set = true;
   }
-  if (conj && scalar_traits<T>::is_complex)
-    spmv_kernel<T, true><<<grid, kThreads, 0, c.stream>>>(A, x, y, coef, prev, ws, want);
-  else
-    spmv_kernel<T, false><<<grid, kThreads, 0, c.stream>>>(A, x, y, coef, prev, ws, want);
+  const bool cj = conj && scalar_traits<T>::is_complex;
+  if (A.n_long > 0) {
+    if (cj) spmv_long_kernel<T, true><<<A.n_long, kLongThreads, 0, c.stream>>>(A, x, y, coef, prev);
+    else spmv_long_kernel<T, false><<<A.n_long, kLongThreads, 0, c.stream>>>(A, x, y, coef, prev);
+    PB_LAUNCH_CHECK();
+    c.ctr.launches += 1;
+  }
+  if (cj) spmv_kernel<T, true><<<grid, kThreads, 0, c.stream>>>(A, x, y, coef, prev, ws, want);
+  else spmv_kernel<T, false><<<grid, kThreads, 0, c.stream>>>(A, x, y, coef, prev, ws, want);
   PB_LAUNCH_CHECK();
   c.ctr.launches += 1;
   if (nrm) c.complete_reduce(*nrm, 1);
+}
+
+// Rows with more than half a slice of non-zeros (handled by spmv_long_kernel), ascending.
+std::vector<int> csr_long_rows(const int* rp, int rows, int nb) {
+  std::vector<int> out;
+  for (int i = 0; i < rows; ++i)
+    if (rp[i + 1] - rp[i] > nb / 2) out.push_back(i);
+  return out;
 }
 
 // Lanes per row for a matrix with `nnz` non-zeros in `rows` rows: the largest row group (32/LPR rows) whose

@@ -261,3 +261,36 @@ def test_medium_synthetic_matches_oracle(oracle):
     check_triplets(A, got, 1e-10, np.float64)
     assert subspace_dist(got["V"], ref["V"]) < 1e-5
     op.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype", [np.float64, np.complex128, np.float32])
+def test_powerlaw_rows_lansvd(oracle, dtype):
+    """BASELINE config 4 in miniature: power-law row lengths (rows of 600..2400 non-zeros next to empty and short rows), so
+    the SpMV's long-row kernel, the run packing around long rows and the fused norm all take part in a full solve."""
+    from propack_b200 import f77
+    rng = np.random.default_rng(4)
+    m, n = 3000, 2600
+    lens = np.minimum(rng.zipf(2.0, size=m) * 3, 2400)
+    lens[:4] = [2400, 700, 0, 129]
+    lens[m // 2] = 600
+    rows = np.repeat(np.arange(m), lens)
+    cols = rng.integers(0, n, size=rows.size)
+    vals = rng.standard_normal(rows.size)
+    if np.issubdtype(dtype, np.complexfloating):
+        vals = vals + 1j * rng.standard_normal(rows.size)
+    A = sp.csr_array(sp.coo_array((vals, (rows, cols)), shape=(m, n))).astype(dtype)
+    A.sum_duplicates(); A.sort_indices()
+    u0 = rng.uniform(size=m).astype(dtype)
+    op = f77.Operator(A)
+    k = 6
+    got = f77.lansvd(op, k, 150, tol=1e-10 if dtype != np.float32 else 1e-5, u0=u0, cgs=True)
+    ref = oracle.lansvd(A, k, 150, tol=1e-10 if dtype != np.float32 else 1e-5, u0=u0, cgs=True, dtype=dtype)
+    sd = np.linalg.svd(A.toarray().astype(np.complex128 if np.iscomplexobj(A.data) else np.float64), compute_uv=False)[:k]
+    tol = 1e-10 if dtype != np.float32 else 1e-4
+    assert got["info"] == 0 and got["k"] == k
+    assert relerr(got["sigma"], sd) < tol
+    assert relerr(got["sigma"], ref["sigma"]) < tol
+    res = np.max(np.linalg.norm(A @ got["V"] - got["U"] * got["sigma"], axis=0))
+    assert res < (1e-8 if dtype != np.float32 else 1e-2) * got["sigma"][0]
+    op.close()
