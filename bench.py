@@ -46,15 +46,44 @@ WORKLOADS = {
 WORKLOADS["c4"] = (2_000_000, 2_000_000, "powerlaw", 64, 700, 1e-10)        # BASELINE configs[3]: complex16, ZLANSVD
 WORKLOADS["c4-small"] = (200_000, 200_000, "powerlaw", 32, 400, 1e-10)
 COMPLEX = {"c4", "c4-small"}
-IRL_P = {"c5": 200, "c5-small": 200}   # workloads solved with DLANSVD_IRL: shifts per restart (kmax column = dim)
+# BASELINE configs[2] ("C3"): dense tall-skinny 2M x 4096 (65.5 GB, generated on the device), k=100, DLANSVD_IRL dim=200 p=100
+WORKLOADS["c3"] = (2_000_000, 4096, "dense", 100, 200, 1e-10)
+WORKLOADS["c3-small"] = (200_000, 1024, "dense", 50, 100, 1e-10)
+DENSE = {"c3", "c3-small"}
+DENSE_SEED = 0
+DENSE_CPU_ROWS = {"c3": 100_000, "c3-small": 20_000}   # rows of the CPU arm's replica (cost per step is linear in rows)
+IRL_P = {"c5": 200, "c5-small": 200, "c3": 100, "c3-small": 50}   # workloads solved with DLANSVD_IRL: shifts per restart (kmax column = dim)
 IRL_MAXITER = 50
 CPU_SAMPLE_STEPS = 150  # Lanczos steps of the same problem the CPU baseline runs per sample
+
+
+class DenseSpec:
+    """The synthetic dense operator of config 3: never materialised on the host at full size (propack_b200/synth.py)."""
+
+    def __init__(self, m, n, table):
+        self.shape, self.table, self.dtype, self.nnz = (m, n), table, np.dtype(np.float64), m * n
+
+    def replica(self, rows):
+        from propack_b200 import synth
+        return synth.dense_planted(self.shape[0], self.shape[1], DENSE_SEED, self.table, rows=np.arange(rows))
+
+
+def make_operator(A):
+    """Device-resident operator for a workload matrix."""
+    from propack_b200 import f77, synth
+    if isinstance(A, DenseSpec):
+        return synth.device_dense_planted(A.shape[0], A.shape[1], DENSE_SEED, A.table)
+    return f77.Operator(A)
 
 
 def make_matrix(name):
     import scipy.sparse as sp
     m, n, dens, k, kmax, tol = WORKLOADS[name]
     rng = np.random.default_rng(0)
+    if dens == "dense":
+        from propack_b200 import synth
+        A = DenseSpec(m, n, synth.planted_table(synth.planted_coefficients(m, n)))
+        return A, np.random.default_rng(1).uniform(size=m), k, kmax, tol
     if dens == "powerlaw":   # SURVEY 8(d) C4: row lengths min(1 + floor(Zipf(2)), 10000), renormalised to ~10 per row, complex values
         lens = np.minimum(rng.zipf(2.0, size=m), 10_000).astype(np.float64)
         lens = np.maximum(1, np.rint(lens * (10.0 * m / lens.sum()))).astype(np.int64)
@@ -168,19 +197,35 @@ def cpu_sample(A, u0, steps):
     return O.stats()["nsteps"] / dt, dt, int(L.oracle_num_threads())
 
 
+def cpu_arm(name, A, u0, steps):
+    """CPU arm on the workload (sparse: the same matrix; dense config 3: a row-scaled replica, rate scaled back).
+    Returns (steps/s on the full problem, seconds, cores, note)."""
+    if isinstance(A, DenseSpec):
+        rows = min(DENSE_CPU_ROWS[name], A.shape[0])
+        Ar = A.replica(rows)
+        v, dt, cores = cpu_sample(Ar, u0[:rows], steps)
+        scale = rows / A.shape[0]
+        return v * scale, dt, cores, (f"dense replica with the first {rows} of {A.shape[0]} rows (the full matrix is 65.5 GB and is only ever "
+                                      f"generated on the device); measured {v:.1f} steps/s on the replica, scaled by {scale:.4f} because every "
+                                      f"per-step cost is linear in the row count")
+    v, dt, cores = cpu_sample(A, u0, steps)
+    return v, dt, cores, ""
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     A, u0, k, kmax, tol = make_matrix(args.workload)
     vals, secs, cores = [], [], 1
+    note = ""
     for i in range(args.warmup + args.steps):
-        v, dt, cores = cpu_sample(A, u0, CPU_SAMPLE_STEPS)
+        v, dt, cores, note = cpu_arm(args.workload, A, u0, CPU_SAMPLE_STEPS)
         if i >= args.warmup:
             vals.append(v); secs.append(dt)
     value = float(np.mean(vals))
     sample = (f"oracle DLANBPRO (C++/OpenMP port of the reference; Fortran not buildable here), first {CPU_SAMPLE_STEPS} "
-              f"Lanczos steps of the {args.workload} problem incl. partial reorthogonalisation, OpenMP CSR/CSC APROD")
+              f"Lanczos steps of the {args.workload} problem incl. partial reorthogonalisation, OpenMP CSR/CSC APROD" + ("; " + note if note else ""))
     line = {
         "impl": "reference", "metric": "lanczos_steps_per_s", "value": value, "unit": "steps/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * float(np.mean(secs)), "higher_is_better": True,
@@ -193,6 +238,12 @@ def run_reference(args):
 
 
 def config_dict(name, A, k, kmax, tol):
+    if name in DENSE:
+        return {"workload": f"BASELINE configs[2] '{name}': synthetic dense {A.shape[0]}x{A.shape[1]} f64 generated on the device "
+                            f"(uniform(-1,1) bulk + planted rank-128 part, propack_b200/synth.py), k={k}, DLANSVD_IRL double dim={kmax} "
+                            f"p={IRL_P[name]}, tol={tol:g}, CGS, ELR",
+                "driver": "dlansvd_irl", "k": k, "kmax": kmax, "tol": tol, "nnz": int(A.nnz), "rows": int(A.shape[0]),
+                "cols": int(A.shape[1]), "l2_policy": "inputs larger than L2 (no flush needed)"}
     irl = name in IRL_P
     cz = name in COMPLEX
     which = "configs[4]" if irl else ("configs[3]" if cz else "configs[1]")
@@ -249,7 +300,7 @@ def run_ours(args):
 
     A, u0, k, kmax, tol = make_matrix(args.workload)
     m, n = A.shape
-    op = f77.Operator(A)                       # matrix resident in HBM from here on
+    op = make_operator(A)                      # matrix resident in HBM from here on
     lanmax = min(m + 1, n + 1, kmax)
     solver = _lib.check(L.propack_b200_solver_create(C.c_int(op.handle), C.c_int(lanmax + 1), C.c_int(lanmax)), "solver_create")
     eps = np.finfo(np.float64).eps
@@ -310,12 +361,17 @@ def run_ours(args):
         iso[f"spmv_{'t' if adj else 'n'}_gbs"] = (op.bytes_per_product(bool(adj)) + float(w) * (n if adj else m)) / (t_ms * 1e-3) / 1e9
 
     # ---- e2e: Fortran-ABI dlansvd_ with host buffers (matrix upload, start vector up, U/V/sigma down) --------
-    rp = np.ascontiguousarray(A.indptr, dtype=np.int32); ci = np.ascontiguousarray(A.indices, dtype=np.int32)
-    va = np.ascontiguousarray(A.data)
+    dense = isinstance(A, DenseSpec)
     pfx = "z" if args.workload in COMPLEX else "d"
     tdt = torch.complex128 if pfx == "z" else torch.float64
     pin = lambda a: torch.from_numpy(a).pin_memory().numpy()
-    rp, ci, va, u0p = pin(rp), pin(ci), pin(va), pin(u0)
+    if dense:   # the 65.5 GB operator has no host copy: e2e = generate it on the device + solve + results to the host
+        rp = ci = va = np.zeros(0)
+        u0p = pin(u0)
+    else:
+        rp = np.ascontiguousarray(A.indptr, dtype=np.int32); ci = np.ascontiguousarray(A.indices, dtype=np.int32)
+        va = np.ascontiguousarray(A.data)
+        rp, ci, va, u0p = pin(rp), pin(ci), pin(va), pin(u0)
     # caller-owned result buffers of the Fortran interface, in pinned memory (allocated once, outside the timed region)
     Upin = torch.empty((k + 1, m), dtype=tdt).pin_memory().numpy().T
     Vpin = torch.empty((k + 1, n), dtype=tdt).pin_memory().numpy().T
@@ -324,13 +380,17 @@ def run_ours(args):
 
     def solve_e2e():
         t0 = time.perf_counter()
-        op2 = f77.Operator.__new__(f77.Operator)
-        h = _lib.check(getattr(L, f"propack_b200_csr_create_{pfx}")(C.c_int(m), C.c_int(n), rp.ctypes.data_as(C.c_void_p),
-                                                                    ci.ctypes.data_as(C.c_void_p), va.ctypes.data_as(C.c_void_p), C.c_int(0)),
-                       "csr_create")
+        if dense:
+            op2 = make_operator(A)
+            torch.cuda.synchronize()
+        else:
+            op2 = f77.Operator.__new__(f77.Operator)
+            h = _lib.check(getattr(L, f"propack_b200_csr_create_{pfx}")(C.c_int(m), C.c_int(n), rp.ctypes.data_as(C.c_void_p),
+                                                                        ci.ctypes.data_as(C.c_void_p), va.ctypes.data_as(C.c_void_p), C.c_int(0)),
+                           "csr_create")
+            op2.handle, op2._cb, op2.dtype, op2.pfx, op2.shape = h, None, np.dtype(A.dtype), pfx, (m, n)
+            op2.iparm = np.array([h, 0], dtype=np.int32); op2.parm = np.zeros(2, dtype=A.dtype)
         e2e_create.append(time.perf_counter() - t0)
-        op2.handle, op2._cb, op2.dtype, op2.pfx, op2.shape = h, None, np.dtype(A.dtype), pfx, (m, n)
-        op2.iparm = np.array([h, 0], dtype=np.int32); op2.parm = np.zeros(2, dtype=A.dtype)
         if args.workload in IRL_P:
             r = f77.lansvd_irl(op2, k, kmax, p=IRL_P[args.workload], maxiter=IRL_MAXITER, tol=tol, u0=u0p, cgs=True, U=Upin, V=Vpin)
         else:
@@ -341,6 +401,8 @@ def run_ours(args):
         return dt, r
 
     _lib.check(L.propack_b200_solver_destroy(C.c_int(solver)), "solver_destroy")  # free the resident bases first
+    if dense:
+        op.close()   # one 65.5 GB operator at a time
     e2e_t, e2e_steps = [], 0
     for i in range(1 + max(1, min(args.steps, 3))):
         propack_b200.reset_counters()
@@ -352,17 +414,17 @@ def run_ours(args):
         t = torch.tensor([float(np.sum(e2e_t))], device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX)
         s = torch.tensor([float(e2e_steps)], device="cuda"); dist.all_reduce(s)
         e2e_val = float(s.item()) / float(t.item())
-    h2d = rp.nbytes + ci.nbytes + va.nbytes + u0.nbytes
+    h2d = rp.nbytes + ci.nbytes + va.nbytes + u0.nbytes + (A.table.nbytes if dense else 0)
     d2h = (m + n) * k * w + 2 * k * 8
 
     # ---- cpu baseline (rank 0, N=1 only): bounded sample of the same workload on the host cores --------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        v, dt, cores = cpu_sample(A, u0, CPU_SAMPLE_STEPS)
+        v, dt, cores, note = cpu_arm(args.workload, A, u0, CPU_SAMPLE_STEPS)
         cpu = {"value": v, "unit": "steps/s", "cores": cores, "kind": "port",
                "sample": f"oracle DLANBPRO (C++/OpenMP port; the Fortran reference cannot be compiled in this image), first "
                          f"{CPU_SAMPLE_STEPS} Lanczos steps of the same problem ({dt:.1f} s); early steps reorthogonalise against "
-                         f"fewer columns than the run average, so this overstates the CPU rate"}
+                         f"fewer columns than the run average, so this overstates the CPU rate" + ("; " + note if note else "")}
     if rank == 0:
         ctr, sigma, kc, info = last
         line = {

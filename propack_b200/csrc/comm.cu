@@ -88,11 +88,55 @@ void Comm::init(int rank_, int world_, const void* id128) {
   ncclComm_t c;
   nccl_check(g_nccl.CommInitRank(&c, world_, id, rank_), "ncclCommInitRank");
   comm_ = c; rank = rank_; world = world_;
+  // Fused collectives over NVLink peer memory (default on; PROPACK_B200_FUSED_COLLECTIVES=0 keeps every reduction on NCCL)
+  const char* e = std::getenv("PROPACK_B200_FUSED_COLLECTIVES");
+  if (world <= kMaxRanks && !(e && e[0] == '0')) {
+    slots = alloc_window(sizeof(PeerSlot) * kMaxRanks * 64);
+    peer_ok = true;
+  }
 }
 
 void Comm::finalize() {
+  if (peer_ok) { free_window(slots); peer_ok = false; }
   if (comm_) { g_nccl.CommDestroy((ncclComm_t)comm_); comm_ = nullptr; }
   rank = 0; world = 1;
+}
+
+Comm::Window Comm::alloc_window(size_t bytes) {
+  Window w;
+  w.bytes = bytes;
+  void* local = nullptr;
+  PB_CUDA(cudaMalloc(&local, bytes));
+  PB_CUDA(cudaMemset(local, 0, bytes));
+  cudaIpcMemHandle_t mine;
+  PB_CUDA(cudaIpcGetMemHandle(&mine, local));
+  // exchange the handles with an NCCL all-gather (the only out-of-band channel the library owns)
+  cudaIpcMemHandle_t* dev = nullptr;
+  PB_CUDA(cudaMalloc((void**)&dev, sizeof(cudaIpcMemHandle_t) * world));
+  PB_CUDA(cudaMemcpy(dev + rank, &mine, sizeof mine, cudaMemcpyHostToDevice));
+  nccl_check(g_nccl.AllGather(dev + rank, dev, sizeof mine, ncclInt8, (ncclComm_t)comm_, nullptr), "ncclAllGather(ipc handles)");
+  PB_CUDA(cudaDeviceSynchronize());
+  std::vector<cudaIpcMemHandle_t> all(world);
+  PB_CUDA(cudaMemcpy(all.data(), dev, sizeof(cudaIpcMemHandle_t) * world, cudaMemcpyDeviceToHost));
+  cudaFree(dev);
+  for (int r = 0; r < world; ++r) {
+    if (r == rank) { w.base[r] = local; continue; }
+    PB_CUDA(cudaIpcOpenMemHandle(&w.base[r], all[r], cudaIpcMemLazyEnablePeerAccess));
+  }
+  PB_CUDA(cudaMalloc((void**)&w.table_dev, sizeof(void*) * kMaxRanks));
+  PB_CUDA(cudaMemcpy(w.table_dev, w.base, sizeof(void*) * kMaxRanks, cudaMemcpyHostToDevice));
+  return w;
+}
+
+void Comm::free_window(Window& w) {
+  for (int r = 0; r < world; ++r) {
+    if (!w.base[r]) continue;
+    if (r == rank) cudaFree(w.base[r]);
+    else cudaIpcCloseMemHandle(w.base[r]);
+    w.base[r] = nullptr;
+  }
+  if (w.table_dev) cudaFree(w.table_dev);
+  w.table_dev = nullptr;
 }
 
 void Comm::allreduce_sum(double* buf, size_t count, cudaStream_t s) {

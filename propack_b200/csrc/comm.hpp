@@ -27,8 +27,25 @@ class Comm {
   long long n_allreduce = 0, n_allgather = 0;
   double allgather_bytes = 0;
 
+  // ---- NVLink peer memory (CUDA IPC): the transport of the fused collectives ---------------------------------
+  // A window is a cudaMalloc'd buffer of the same size on every rank, mapped into every other rank's address space;
+  // base[r] is rank r's copy as seen from this process (base[rank] = the local one).  Collective call.
+  static constexpr int kMaxRanks = 8;
+  struct Window { void* base[kMaxRanks] = {nullptr}; void** table_dev = nullptr; size_t bytes = 0; };
+  Window alloc_window(size_t bytes);
+  void free_window(Window& w);
+  bool peer_ok = false;          // all peers mapped (set by init when PROPACK_B200_FUSED_COLLECTIVES != 0)
+  Window slots;                  // PeerSlot[kMaxRanks][Context::kSlots]: scalar partials of every rank
+
  private:
   void* comm_ = nullptr;  // ncclComm_t
+};
+
+// One rank's partial of one reduction, written by that rank into every peer's `slots` window.
+struct PeerSlot {
+  double re, im;
+  volatile unsigned long long seq;
+  unsigned long long pad;
 };
 
 // Block partition of a dimension over `world` ranks: every rank owns `shard_slice(dim, world)` consecutive

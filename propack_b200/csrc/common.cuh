@@ -164,7 +164,20 @@ struct ReduceWs {              // workspace of one in-flight grid reduction
   unsigned long long seq;      // sequence number this launch publishes
   int local_only;              // row-sharded run: store this rank's raw partial in dev_slot only; the host-side
                                // Context::complete_reduce() all-reduces it across ranks and publishes
+  // fused cross-rank reduction over NVLink peer memory (row-sharded run with mapped peers): the last CTA writes this
+  // rank's partial into every rank's window, waits for the other ranks' partials in its own, sums them in rank order
+  // (identical on every rank) and publishes -- no NCCL call, no extra launch.
+  void** peer_table;           // device array: peer_table[r] = rank r's PeerSlot window, or null
+  int rank, world, slot;
+  volatile unsigned int* host_err;  // mapped pinned error word (set when a peer never shows up)
 };
+
+struct PeerSlotDev {           // layout of comm.hpp::PeerSlot
+  double re, im;
+  unsigned long long seq;
+  unsigned long long pad;
+};
+constexpr int kPeerSlotsPerRank = 64;
 
 // Called by every thread of every CTA; `v` = this CTA's partial (valid in thread 0; real part
 // and imag part for complex dots).  kind: 0 = store sum, 1 = store sqrt(sum) (norms).
@@ -189,7 +202,37 @@ __device__ inline void grid_publish(double vre, double vim, const ReduceWs& ws, 
   sr = block_sum(sr, red_smem);
   si = block_sum(si, red_smem);
   if (threadIdx.x == 0) {
-    if (ws.local_only) {
+    if (ws.peer_table != nullptr) {
+      // ---- one-shot all-reduce over peer memory ----------------------------------------------------------
+      for (int p = 0; p < ws.world; ++p) {
+        PeerSlotDev* d = static_cast<PeerSlotDev*>(ws.peer_table[p]) + ws.rank * kPeerSlotsPerRank + ws.slot;
+        d->re = sr; d->im = si;
+      }
+      __threadfence_system();
+      for (int p = 0; p < ws.world; ++p) {
+        PeerSlotDev* d = static_cast<PeerSlotDev*>(ws.peer_table[p]) + ws.rank * kPeerSlotsPerRank + ws.slot;
+        *reinterpret_cast<volatile unsigned long long*>(&d->seq) = ws.seq;
+      }
+      double tr = 0.0, ti = 0.0;
+      const long long t0 = clock64();
+      bool dead = false;
+      for (int q = 0; q < ws.world; ++q) {
+        PeerSlotDev* m = static_cast<PeerSlotDev*>(ws.peer_table[ws.rank]) + q * kPeerSlotsPerRank + ws.slot;
+        while (*reinterpret_cast<volatile unsigned long long*>(&m->seq) != ws.seq) {
+          if (clock64() - t0 > 20000000000LL) { dead = true; break; }   // ~10 s: a peer died; do not hang the GPU
+        }
+        if (dead) break;
+        __threadfence();
+        tr += *reinterpret_cast<volatile double*>(&m->re);
+        ti += *reinterpret_cast<volatile double*>(&m->im);
+      }
+      if (dead) { *ws.host_err = 1u; tr = ti = 0.0; }
+      if (kind == 1) tr = sqrt(tr);
+      ws.dev_slot->re = tr; ws.dev_slot->im = ti;
+      ws.host_slot->re = tr; ws.host_slot->im = ti;
+      __threadfence_system();
+      ws.host_slot->seq = ws.seq;
+    } else if (ws.local_only) {
       ws.dev_slot->re = sr; ws.dev_slot->im = si;
     } else {
       if (kind == 1) sr = sqrt(sr);

@@ -32,6 +32,9 @@ Context::Context() {
   PB_CUDA(cudaHostAlloc((void**)&host_slots, sizeof(ScalarSlot) * kSlots, cudaHostAllocMapped));
   std::memset((void*)host_slots, 0, sizeof(ScalarSlot) * kSlots);
   PB_CUDA(cudaHostGetDevicePointer((void**)&host_slots_dev, (void*)host_slots, 0));
+  PB_CUDA(cudaHostAlloc((void**)&host_err, sizeof(unsigned int), cudaHostAllocMapped));
+  *host_err = 0u;
+  PB_CUDA(cudaHostGetDevicePointer((void**)&host_err_dev, (void*)host_err, 0));
   PB_CUDA(cudaMalloc((void**)&dev_slots, sizeof(ScalarSlot) * kSlots));
   PB_CUDA(cudaMemset(dev_slots, 0, sizeof(ScalarSlot) * kSlots));
   PB_CUDA(cudaMalloc((void**)&partials, sizeof(double) * 2 * kMaxCtas));
@@ -62,6 +65,10 @@ double Context::wait(const Pending& p, double* imag) {
       }
       if (e != cudaErrorNotReady) cuda_check(e, "cudaStreamQuery while waiting for a scalar", __FILE__, __LINE__);
     }
+  }
+  if (*(volatile unsigned int*)host_err) {
+    *host_err = 0u;
+    throw CudaError(cudaErrorUnknown, "propack_b200: a peer rank never delivered its partial of a cross-GPU reduction (timeout)");
   }
   if (imag) *imag = s->im;
   return s->re;

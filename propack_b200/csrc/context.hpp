@@ -36,7 +36,7 @@ class Context {
   bool profile = false;        // per-phase CUDA-event timing (adds syncs; off for benchmarks)
 
   // --- scalar slots -------------------------------------------------------------------------
-  static constexpr int kSlots = 64;
+  static constexpr int kSlots = 64;   // == kPeerSlotsPerRank
   ScalarSlot* host_slots = nullptr;      // pinned + mapped
   ScalarSlot* host_slots_dev = nullptr;  // device view of the same memory
   ScalarSlot* dev_slots = nullptr;
@@ -55,10 +55,18 @@ class Context {
     ReduceWs ws;
     ws.partials = partials; ws.ticket = ticket;
     ws.dev_slot = dev_slots + s; ws.host_slot = host_slots_dev + s; ws.seq = ++seq;
+    ws.peer_table = nullptr; ws.rank = 0; ws.world = 1; ws.slot = s; ws.host_err = host_err_dev;
     ws.local_only = dist_reduce ? 1 : 0;
+    if (dist_reduce && peer_table) {   // fused path: the kernel itself completes the cross-rank reduction
+      ws.peer_table = peer_table; ws.rank = peer_rank; ws.world = peer_world; ws.local_only = 0;
+    }
     p->slot = s; p->seq = ws.seq; p->local_only = ws.local_only;
     return ws;
   }
+  // set by Comm-aware code (c_api: comm_init) when peer windows are mapped
+  void** peer_table = nullptr; int peer_rank = 0, peer_world = 1;
+  unsigned int* host_err = nullptr;      // pinned + mapped error word
+  unsigned int* host_err_dev = nullptr;
   // Call right after launching the kernel that owns `p`.  kind: 0 = sum (dot products), 1 = sqrt(sum) (norms).
   // Single-GPU: nothing to do (the kernel's last CTA already published).
   void complete_reduce(const Pending& p, int kind);

@@ -294,3 +294,36 @@ def test_powerlaw_rows_lansvd(oracle, dtype):
     res = np.max(np.linalg.norm(A @ got["V"] - got["U"] * got["sigma"], axis=0))
     assert res < (1e-8 if dtype != np.float32 else 1e-2) * got["sigma"][0]
     op.close()
+
+
+@pytest.mark.gpu
+def test_dense_synthetic_generator_bit_exact_and_irl(oracle):
+    """BASELINE config 3 in miniature: the on-device dense generator equals its numpy replica bit for bit (unit-vector
+    products return exact columns / rows), and DLANSVD_IRL on it matches dense LAPACK SVD and the oracle."""
+    from propack_b200 import f77, synth
+    m, n, seed = 3001, 200, 7
+    T = synth.planted_table(synth.planted_coefficients(m, n))
+    A = synth.dense_planted(m, n, seed, T)
+    op = synth.device_dense_planted(m, n, seed, T)
+    for j in (0, 1, 63, 64, 199):
+        e = np.zeros(n); e[j] = 1.0
+        assert np.array_equal(f77.aprod(op, "n", e), A[:, j])
+    for i in (0, 255, 256, 3000):
+        e = np.zeros(m); e[i] = 1.0
+        assert np.array_equal(f77.aprod(op, "t", e), A[i, :])
+    rng = np.random.default_rng(0)
+    x = rng.standard_normal(n)
+    assert rel_vec(f77.aprod(op, "n", x), A @ x) < 1e-13
+    u0 = rng.uniform(size=m)
+    k = 10
+    got = f77.lansvd_irl(op, k, 40, p=20, maxiter=100, tol=1e-10, u0=u0, cgs=True)
+    ref = oracle.lansvd_irl(A, k, 40, p=20, maxiter=100, tol=1e-10, u0=u0, cgs=True)
+    sd = np.linalg.svd(A, compute_uv=False)[:k]
+    assert got["info"] == 0 and got["k"] == k
+    assert relerr(got["sigma"], sd) < 1e-10 and relerr(got["sigma"], ref["sigma"]) < 1e-10
+    assert np.max(np.linalg.norm(A @ got["V"] - got["U"] * got["sigma"], axis=0)) < 1e-8 * got["sigma"][0]
+    op.close()
+
+
+def rel_vec(a, b):
+    return float(np.linalg.norm(np.asarray(a) - np.asarray(b)) / np.linalg.norm(np.asarray(b)))

@@ -1,7 +1,8 @@
 #!/bin/bash
-# multi-GPU parity check (run with gpurun --gpus N)
+# multi-GPU parity check (run with gpurun --gpus N): fused peer-memory collectives (default) and the NCCL-only path
 mkdir -p gpurun_out
 N=${1:-2}
-nvidia-smi --query-gpu=index,name --format=csv > gpurun_out/dist_gpus.txt
-NCCL_DEBUG=WARN timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 tests/dist_check.py > gpurun_out/dist_check_$N.log 2>&1; echo "rc=$?" >> gpurun_out/dist_check_$N.log
-tail -30 gpurun_out/dist_check_$N.log
+for FUSED in 1 0; do
+  PROPACK_B200_FUSED_COLLECTIVES=$FUSED timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 2951$FUSED tests/dist_check.py > gpurun_out/dist_check_${N}_fused$FUSED.log 2>&1; echo "rc=$?" >> gpurun_out/dist_check_${N}_fused$FUSED.log
+  grep -E "dist_check|DIST_CHECK|rc=|rror" gpurun_out/dist_check_${N}_fused$FUSED.log | tail -12
+done

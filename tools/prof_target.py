@@ -14,7 +14,7 @@ wl = sys.argv[1] if len(sys.argv) > 1 else "c2"
 A, u0, k, kmax, tol = bench.make_matrix(wl)
 L = _lib.lib()
 _lib.check(L.propack_b200_init(), "init")
-op = f77.Operator(A)
+op = bench.make_operator(A)
 L.propack_b200_bench_reorth_d.argtypes = [C.c_long, C.c_int, C.c_int, C.c_int]
 L.propack_b200_bench_gemm_d.argtypes = [C.c_long, C.c_int, C.c_int, C.c_int]
 m = A.shape[0]
