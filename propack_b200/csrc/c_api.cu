@@ -170,10 +170,7 @@ int csr_create_sharded(int mg, int ng, const int* row_rp, const int* row_ci, con
   };
   upload(ml, ng, row_rp, row_ci, row_va, op->rp, op->ci, op->va, op->A, op->ld_n * cm.world, op->lrows);
   upload(nl, mg, colt_rp, colt_ci, colt_va, op->trp, op->tci, op->tva, op->At, op->ld_m * cm.world, op->tlrows);
-  op->xfull_n.alloc((size_t)op->ld_n * cm.world);
-  op->xfull_m.alloc((size_t)op->ld_m * cm.world);
-  PB_CUDA(cudaMemset(op->xfull_n.p, 0, sizeof(T) * op->xfull_n.n));
-  PB_CUDA(cudaMemset(op->xfull_m.p, 0, sizeof(T) * op->xfull_m.n));
+  op->alloc_gather_buffers();
   OpEntry e; e.tag = abi<T>::tag; e.kind = 2; e.op = op;
   const int h = g_next_op++;
   g_ops[h] = e;

@@ -48,6 +48,10 @@ template <class T> struct LinOp {
   virtual ~LinOp() {}
   virtual void apply(Context& c, bool adjoint, const T* x, T* y, R coef, const T* prev, Pending* nrm) = 0;
   virtual double algorithmic_bytes(bool adjoint) const = 0;  // per apply, SURVEY 8d byte model
+  // Row-sharded operators may fuse "x <- scale*x" with the all-gather the next apply(adjoint, x, ...) needs.
+  // Returns false when not supported (the caller scales x itself and apply() gathers).
+  virtual bool stage_scaled(Context&, bool /*adjoint*/, R /*scale*/, T* /*x*/) { return false; }
+  virtual void invalidate_staged() {}
 };
 
 template <class T> struct CsrOperator : LinOp<T> {
@@ -74,17 +78,59 @@ template <class T> struct CsrOperator : LinOp<T> {
 template <class T> struct ShardedCsrOperator : LinOp<T> {
   using R = real_t<T>;
   DeviceBuffer<int> rp, ci, trp, tci, lrows, tlrows;
-  DeviceBuffer<T> va, tva, xfull_n, xfull_m;
+  DeviceBuffer<T> va, tva, xbuf_n, xbuf_m;
   CsrDevice<T> A, At;  // A: m_loc x (world*ld_n);  At: n_loc x (world*ld_m)
+  // gather buffers: [world*ld elements | kMaxRanks arrival flags]; peer windows when NVLink peer memory is mapped
+  // (index 0: the n-vector gathered for A x, index 1: the m-vector gathered for A^H x)
+  T* xfull[2] = {nullptr, nullptr};
+  Comm::Window win[2];
+  bool fused = false;
+  const T* staged_ptr[2] = {nullptr, nullptr};
+  bool staged_valid[2] = {false, false};
+  unsigned long long epoch[2] = {0, 0};
+  long ld_of(int d) const { return d ? this->ld_m : this->ld_n; }
+  void alloc_gather_buffers() {
+    Comm& cm = Comm::get();
+    fused = cm.peer_ok;
+    for (int d = 0; d < 2; ++d) {
+      const size_t bytes = sizeof(T) * (size_t)ld_of(d) * cm.world + sizeof(unsigned long long) * Comm::kMaxRanks;
+      if (fused) { win[d] = cm.alloc_window(bytes); xfull[d] = static_cast<T*>(win[d].base[cm.rank]); }
+      else {
+        DeviceBuffer<T>& b = d ? xbuf_m : xbuf_n;
+        b.alloc(bytes / sizeof(T) + 1);
+        PB_CUDA(cudaMemset(b.p, 0, bytes));
+        xfull[d] = b.p;
+      }
+    }
+  }
+  ~ShardedCsrOperator() override {
+    if (fused) { cudaDeviceSynchronize(); Comm& cm = Comm::get(); cm.free_window(win[0]); cm.free_window(win[1]); }
+  }
+  const unsigned long long* flags(int d) const {
+    return reinterpret_cast<const unsigned long long*>(xfull[d] + (size_t)ld_of(d) * Comm::get().world);
+  }
+  bool stage_scaled(Context& c, bool adjoint, R scale, T* x) override {
+    if (!fused) return false;
+    const int d = adjoint ? 1 : 0;
+    Comm& cm = Comm::get();
+    epoch[d] += 1;
+    k_scal_push<T>(c, adjoint ? this->m : this->n, ld_of(d), x, scale, win[d].table_dev, cm.rank, cm.world, epoch[d]);
+    staged_ptr[d] = x; staged_valid[d] = true;
+    return true;
+  }
+  void invalidate_staged() override { staged_valid[0] = staged_valid[1] = false; }
   void apply(Context& c, bool adjoint, const T* x, T* y, R coef, const T* prev, Pending* nrm) override {
     Comm& cm = Comm::get();
-    if (adjoint) {
-      cm.allgather(x, xfull_m.p, sizeof(T) * (size_t)this->ld_m, c.stream);
-      k_spmv<T>(c, At, /*conj=*/true, xfull_m.p, y, coef, prev, nrm);
+    const int d = adjoint ? 1 : 0;
+    if (staged_valid[d] && staged_ptr[d] == x && nrm != nullptr) {
+      // the slices were pushed by the producers (stage_scaled); wait for all of them, then a purely local SpMV.
+      // (nrm != nullptr: the cross-rank norm reduction that follows is what makes reusing the buffer safe.)
+      k_wait_flags(c, flags(d), cm.world, epoch[d]);
     } else {
-      cm.allgather(x, xfull_n.p, sizeof(T) * (size_t)this->ld_n, c.stream);
-      k_spmv<T>(c, A, false, xfull_n.p, y, coef, prev, nrm);
+      cm.allgather(x, xfull[d], sizeof(T) * (size_t)ld_of(d), c.stream);
     }
+    staged_valid[d] = false;
+    k_spmv<T>(c, adjoint ? At : A, /*conj=*/adjoint, xfull[d], y, coef, prev, nrm);
   }
   double algorithmic_bytes(bool adjoint) const override {
     const double w = sizeof(T);
@@ -191,6 +237,16 @@ template <class T> class Engine {
       else { mul = ctoc / cfromc; done = true; }
       k_scal<T>(c, len, x, mul);
     }
+  }
+
+  // x <- x/alpha where x is the vector the next apply(adjoint_next, x, ...) consumes: on a row-sharded operator with
+  // mapped peers the scaling kernel also pushes the slice to every rank (fused all-gather); otherwise plain dsafescal.
+  void normalize_for_apply(bool adjoint_next, long len, R alpha, T* x) {
+    if (dist && std::fabs(alpha) >= host::Machine<R>::sfmin) {
+      Context::PhaseScope ps(c, PH_LEVEL1);
+      if (op->stage_scaled(c, adjoint_next, R(1) / alpha, x)) return;
+    }
+    safescal(len, alpha, x);
   }
 
   R nrm2(long len, const T* x) {

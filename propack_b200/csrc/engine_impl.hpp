@@ -17,6 +17,7 @@ template <class T> int Engine<T>::lanbpro(int k0, int& k, R* a, R* b, R& rnorm, 
   const R eps = host::Machine<R>::eps;
   const R eps34 = std::pow(eps, R(0.75));
   DistScope ds(c, dist);
+  op->invalidate_staged();  // vectors may have been modified since the last call (restart, re-entry rescaling)
   const R epsn = R(std::max(mg, ng)) * eps;
   const R epsn2 = std::sqrt(R(std::max(mg, ng))) * eps;
   const bool elr = ioption[1] > 0;
@@ -142,7 +143,7 @@ template <class T> int Engine<T>::lanbpro(int k0, int& k, R* a, R* b, R& rnorm, 
       ierr = j;
     }
     a[j - 1] = alpha;
-    if (alpha != zero) safescal(n, alpha, vcol(j));
+    if (alpha != zero) normalize_for_apply(false, n, alpha, vcol(j));
 
     // ---- beta_{j+1} u_{j+1} = A v_j - alpha_j u_j -------------------------------------------------------
     {
@@ -203,7 +204,7 @@ template <class T> int Engine<T>::lanbpro(int k0, int& k, R* a, R* b, R& rnorm, 
       ierr = j;
     }
     b[j - 1] = beta;
-    if (beta != zero && beta != one) safescal(m, beta, ucol(j + 1));
+    if (beta != zero && beta != one) normalize_for_apply(true, m, beta, ucol(j + 1));
     rnorm = beta;
   }
   doption[2] = anorm;  // :547 (in/out)

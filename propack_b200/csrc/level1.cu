@@ -28,6 +28,43 @@ scal_kernel(long n, T* __restrict__ x, real_t<T> a, const ScalarSlot* slot) {
   }
 }
 
+// Fused "normalise + all-gather" of a row-sharded run: x <- a*x, and the scaled slice is also stored into every
+// rank's gather buffer (peer memory over NVLink; bases[r] = rank r's buffer) at this rank's offset.  The last CTA
+// raises this rank's arrival flag in every buffer once all stores are visible system-wide.
+template <class T>
+__global__ void __launch_bounds__(kThreads)
+scal_push_kernel(long n, long ld, T* __restrict__ x, real_t<T> a, void** bases, int rank, int world, unsigned int* ticket,
+                 unsigned long long epoch) {
+  constexpr int VEC = Pack<T>::N;
+  __shared__ bool is_last;
+  const long np = (n + VEC - 1) / VEC;
+  for (long i = (long)blockIdx.x * kThreads + threadIdx.x; i < np; i += (long)gridDim.x * kThreads) {
+    Pack<T> p = ld_pack(x + i * VEC);
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) p.v[e] = a * p.v[e];  // padding stays 0
+    st_pack(x + i * VEC, p);
+    for (int r = 0; r < world; ++r) st_pack(static_cast<T*>(bases[r]) + (long)rank * ld + i * VEC, p);
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) is_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (is_last && threadIdx.x < world) {
+    unsigned long long* flags = reinterpret_cast<unsigned long long*>(static_cast<T*>(bases[threadIdx.x]) + (long)world * ld);
+    *reinterpret_cast<volatile unsigned long long*>(flags + rank) = epoch;
+    if (threadIdx.x == 0) *ticket = 0u;
+  }
+}
+
+// Consumer side of the fused all-gather: returns once every rank's slice of epoch `epoch` has landed in this rank's buffer.
+__global__ void wait_flags_kernel(const unsigned long long* flags, int world, unsigned long long epoch, volatile unsigned int* host_err) {
+  if ((int)threadIdx.x >= world) return;
+  const long long t0 = clock64();
+  while (*reinterpret_cast<const volatile unsigned long long*>(flags + threadIdx.x) < epoch) {
+    if (clock64() - t0 > 20000000000LL) { *host_err = 1u; break; }   // ~10 s: a peer died; do not hang the GPU
+  }
+}
+
 template <class T>
 __global__ void __launch_bounds__(kThreads)
 zero_kernel(long n, T* __restrict__ x) {
@@ -164,6 +201,17 @@ template <class T> void k_scal_inv_slot(Context& c, long n, T* x, const ScalarSl
   PB_LAUNCH_CHECK();
   c.ctr.launches += 1;
 }
+template <class T>
+void k_scal_push(Context& c, long n, long ld, T* x, real_t<T> a, void** bases_dev, int rank, int world, unsigned long long epoch) {
+  scal_push_kernel<T><<<l1_grid<T>(c, n), kThreads, 0, c.stream>>>(n, ld, x, a, bases_dev, rank, world, c.ticket, epoch);
+  PB_LAUNCH_CHECK();
+  c.ctr.launches += 1;
+}
+void k_wait_flags(Context& c, const unsigned long long* flags, int world, unsigned long long epoch) {
+  wait_flags_kernel<<<1, 32, 0, c.stream>>>(flags, world, epoch, c.host_err_dev);
+  PB_LAUNCH_CHECK();
+  c.ctr.launches += 1;
+}
 template <class T> void k_zero(Context& c, long n, T* x) {
   if (n <= 0) return;
   zero_kernel<T><<<l1_grid<T>(c, n), kThreads, 0, c.stream>>>(n, x);
@@ -205,6 +253,7 @@ template <class T> void k_larnv_nrm(Context& c, long n, T* x, const int iseed[4]
   template void k_scal<T>(Context&, long, T*, real_t<T>);                         \
   template void k_scal_inv_slot<T>(Context&, long, T*, const ScalarSlot*);        \
   template void k_zero<T>(Context&, long, T*);                                    \
+  template void k_scal_push<T>(Context&, long, long, T*, real_t<T>, void**, int, int, unsigned long long); \
   template void k_axpy_nrm<T>(Context&, long, T, const T*, T*, Pending*);         \
   template void k_dotc<T>(Context&, long, const T*, const T*, Pending*);          \
   template void k_nrm2<T>(Context&, long, const T*, Pending*);                    \
