@@ -350,6 +350,29 @@ def run_ours(args):
     achieved = rb / (reorth_ms * 1e-3) / 1e9 if reorth_ms > 0 else 0.0
     spmv_bytes = (pctr["nopx"] / 2.0) * (op.bytes_per_product(False) + op.bytes_per_product(True) + float(w) * (m + n))
     spmv_gbs = spmv_bytes / (ph["aprod"]["ms"] * 1e-3) / 1e9 if ph["aprod"]["ms"] > 0 else 0.0
+    # the roofline object describes the phase with the larger share of the solve (SpMV / dense GEMV as APROD, or the
+    # reorthogonalisation GEMV pair); both are HBM streams, timed with CUDA events on the library stream
+    tot_ms = sum(v["ms"] for v in ph.values())
+    aprod_ms = ph["aprod"]["ms"]
+    # ncu --set full, per launch, C2 operands (profiles/r01_ncu_full_extract.txt): dram read + write
+    traffic_known = {("c2", "spmv"): 140.03e6 + 5.3e6, ("c2", "reorth"): None}
+    if aprod_ms >= reorth_ms:
+        kname = ("dense APROD = gemv_n_kernel / gemv_t_kernel + gemv_t_finalize over A itself" if isinstance(A, DenseSpec) else
+                 "spmv_kernel (CSR gather SpMV, fused axpy + norm; + spmv_long_kernel on power-law rows)")
+        roofline = {"bound": "hbm", "kernel": kname, "achieved": spmv_gbs, "peak": peak, "unit": "GB/s", "frac": spmv_gbs / peak,
+                    "peak_source": peak_src, "frac_of_nominal_8000": spmv_gbs / 8000.0,
+                    "traffic": traffic_known.get((args.workload, "spmv")), "algorithmic_bytes": spmv_bytes,
+                    "algorithmic_bytes_per_launch": spmv_bytes / max(pctr["nopx"], 1), "kernel_ms_in_solve": aprod_ms,
+                    "share_of_solve": aprod_ms / tot_ms,
+                    "note": ("random-column gathers bound this kernel by the L1TEX wavefront rate, not HBM: the measured gather floor is "
+                             "~51% of the HBM peak at 10 nnz/row (profiles/r01_spmv_lab.md)") if not isinstance(A, DenseSpec) else "",
+                    "how": "CUDA-event phase timers on the library stream in one extra profiled solve of the same workload"}
+    else:
+        roofline = {"bound": "hbm", "kernel": "reorthogonalisation GEMV pair (gemv_t_kernel + gemv_t_finalize + gemv_n_kernel)",
+                    "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
+                    "frac_of_nominal_8000": achieved / 8000.0, "traffic": traffic_known.get((args.workload, "reorth")),
+                    "algorithmic_bytes": rb, "kernel_ms_in_solve": reorth_ms, "share_of_solve": reorth_ms / tot_ms,
+                    "how": "CUDA-event phase timers on the library stream in one extra profiled solve of the same workload"}
     # isolated kernels (device-resident synthetic operands, L2 flushed between launches)
     L.propack_b200_bench_reorth_d.argtypes = [C.c_long, C.c_int, C.c_int, C.c_int]
     iso = {}
@@ -440,11 +463,9 @@ def run_ours(args):
                     "time_to_k_triplets_s": float(np.mean(e2e_t)),
                     "operator_create_s": float(np.mean(e2e_create[1:])) if len(e2e_create) > 1 else None,
                     "path": "propack_b200_csr_create_d + dlansvd[_irl]_ (Fortran ABI; host CSR, start vector and the caller's U,V result buffers in pinned memory; U,V,sigma copied back)"},
-            "roofline": {"bound": "hbm", "kernel": "reorthogonalisation GEMV pair (gemv_t_kernel + gemv_t_finalize + gemv_n_kernel)",
-                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
-                         "frac_of_nominal_8000": achieved / 8000.0, "traffic": None,
-                         "algorithmic_bytes": rb, "kernel_ms_in_solve": reorth_ms, "share_of_solve": reorth_ms / sum(v["ms"] for v in ph.values()),
-                         "how": "CUDA-event phase timers on the library stream in one extra profiled solve of the same workload"},
+            "roofline": roofline,
+            "reorth": {"achieved_gbs_in_solve": achieved, "frac": achieved / peak, "reorth_ms_in_solve": reorth_ms,
+                       "algorithmic_bytes": rb},
             "spmv": {"achieved_gbs_in_solve": spmv_gbs, "frac": spmv_gbs / peak, "aprod_ms_in_solve": ph["aprod"]["ms"]},
             "isolated_kernels_gbs": iso,
             "phases_ms": {kname: v["ms"] for kname, v in ph.items()},

@@ -264,7 +264,8 @@ template <class T> class Engine {
   void reorth(long len, int k, const T* basis, long ld, T* vnew, R& normvnew, const host::IntervalList& idx, R kappa,
               int iflag) {
     (void)iflag;
-    if (k <= 0 || len <= 0) return;
+    // (a rank that owns no rows of a sharded vector still takes part in every cross-rank reduction below)
+    if (k <= 0 || (len <= 0 && !dist)) return;
     Context::PhaseScope ps(c, PH_REORTH);
     const int NTRY = 5;
     for (int itry = 0; itry < NTRY; ++itry) {

@@ -327,3 +327,26 @@ def test_dense_synthetic_generator_bit_exact_and_irl(oracle):
 
 def rel_vec(a, b):
     return float(np.linalg.norm(np.asarray(a) - np.asarray(b)) / np.linalg.norm(np.asarray(b)))
+
+
+@pytest.mark.gpu
+def test_c2_full_size_parity_and_properties(oracle):
+    """BASELINE configs[1] at its full size (1M x 1M, 1e7 non-zeros, k=50, kmax=600): sigma against the CPU oracle on the same
+    inputs to 1e-10 relative, and the size-independent properties -- residuals, orthogonality, ordering."""
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+    from propack_b200 import f77
+    A, u0, k, kmax, tol = bench.make_matrix("c2")
+    op = f77.Operator(A)
+    got = f77.lansvd(op, k, kmax, tol=tol, u0=u0, cgs=True)
+    op.close()
+    assert got["info"] == 0 and got["k"] == k
+    S, U, V = got["sigma"], got["U"], got["V"]
+    assert np.all(np.diff(S) <= 0) and S[0] < 10 and S[-1] > 7          # sqrt(10)*(1+1) ~ 6.3 bulk edge + finite-size tail
+    res = np.linalg.norm(A @ V - U * S, axis=0)
+    resT = np.linalg.norm(A.T.tocsr() @ U - V * S, axis=0)
+    assert res.max() < 1e-8 * S[0] and resT.max() < 1e-6 * S[0]
+    assert np.max(np.abs(U.T @ U - np.eye(k))) < 1e-6 and np.max(np.abs(V.T @ V - np.eye(k))) < 1e-6
+    ref = oracle.lansvd(A, k, kmax, tol=tol, u0=u0, cgs=True, jobu=False, jobv=False)
+    assert ref["k"] == k and relerr(S, ref["sigma"]) < 1e-10
