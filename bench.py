@@ -574,8 +574,10 @@ def run_ours_sharded(args):
             "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": wl_dtype(args.workload)[0], "data": "synthetic",
             "config": dict(config_dict(args.workload, A, k, kmax, tol),
-                           parallelism=f"rows of A and U, and V-vectors, block-sharded over {world} GPUs; NCCL all-gather of the "
-                                       f"SpMV input, all-reduce of reorthogonalisation coefficients and norm partials"),
+                           parallelism=f"rows of A and U, and V-vectors, block-sharded over {world} GPUs; all-gather of the SpMV input, "
+                                       f"all-reduce of reorthogonalisation coefficients and norm partials fused into the producing "
+                                       f"kernels over NVLink peer memory (NCCL for the un-staged products); collectives_total counts "
+                                       f"the NCCL calls that remain"),
             "time_to_k_triplets_s": total_ms / args.steps / 1e3, "lanczos_steps_per_solve": ctr["nsteps"], "converged": kc,
             "info": info, "sigma_1": float(sigma[0]) if kc else None, "sigma_k": float(sigma[-1]) if kc else None,
             "gpu_launches": int(launches), "host_syncs_per_solve": ctr["host_syncs"],

@@ -735,13 +735,14 @@ int propack_b200_comm_init(int rank, int world, const void* id128) {
   Comm& cm = Comm::get();
   cm.init(rank, world, id128);
   c.peer_table = cm.peer_ok ? cm.slots.table_dev : nullptr;
+  c.coef_table = cm.peer_ok ? cm.coef.table_dev : nullptr;
   c.peer_rank = cm.rank; c.peer_world = cm.world;
   return 0;
   PB_API_CATCH(return code__)
 }
 int propack_b200_comm_finalize(void) {
   PB_API_TRY
-  try { Context& c = Context::get(); c.sync(); c.peer_table = nullptr; c.peer_rank = 0; c.peer_world = 1; } catch (...) {}
+  try { Context& c = Context::get(); c.sync(); c.peer_table = nullptr; c.coef_table = nullptr; c.peer_rank = 0; c.peer_world = 1; } catch (...) {}
   Comm::get().finalize();
   return 0;
   PB_API_CATCH(return code__)

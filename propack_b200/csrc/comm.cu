@@ -92,12 +92,13 @@ void Comm::init(int rank_, int world_, const void* id128) {
   const char* e = std::getenv("PROPACK_B200_FUSED_COLLECTIVES");
   if (world <= kMaxRanks && !(e && e[0] == '0')) {
     slots = alloc_window(sizeof(PeerSlot) * kMaxRanks * 64);
+    coef = alloc_window(2 * kCoefBufBytes + 2 * kMaxRanks * sizeof(unsigned long long));
     peer_ok = true;
   }
 }
 
 void Comm::finalize() {
-  if (peer_ok) { free_window(slots); peer_ok = false; }
+  if (peer_ok) { free_window(slots); free_window(coef); peer_ok = false; }
   if (comm_) { g_nccl.CommDestroy((ncclComm_t)comm_); comm_ = nullptr; }
   rank = 0; world = 1;
 }

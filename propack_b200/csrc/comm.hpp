@@ -36,6 +36,10 @@ class Comm {
   void free_window(Window& w);
   bool peer_ok = false;          // all peers mapped (set by init when PROPACK_B200_FUSED_COLLECTIVES != 0)
   Window slots;                  // PeerSlot[kMaxRanks][Context::kSlots]: scalar partials of every rank
+  // reorthogonalisation coefficients: 2 buffers x [kMaxRanks][kCoefMax] 16-byte elements, then 2 x kMaxRanks flags
+  static constexpr int kCoefMax = 2048;
+  static constexpr size_t kCoefBufBytes = (size_t)kMaxRanks * kCoefMax * 16;
+  Window coef;
 
  private:
   void* comm_ = nullptr;  // ncclComm_t

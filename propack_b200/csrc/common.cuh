@@ -95,6 +95,12 @@ template <class R> __device__ inline void fnma_(cplx<R>& acc, cplx<R> a, cplx<R>
 // 128-bit packs: every bulk HBM access in the reorthogonalisation / level-1 kernels is one
 // LDG.128 / STG.128 per lane (device columns are 256-byte aligned, leading dims padded).
 // --------------------------------------------------------------------------------------------
+__device__ inline float ld_volatile(const volatile float* p) { return *p; }
+__device__ inline double ld_volatile(const volatile double* p) { return *p; }
+template <class R> __device__ inline cplx<R> ld_volatile(const volatile cplx<R>* p) {
+  return cplx<R>(*reinterpret_cast<const volatile R*>(&p->x), *reinterpret_cast<const volatile R*>(&p->y));
+}
+
 template <class T> struct alignas(16) Pack {
   static constexpr int N = 16 / sizeof(T);
   T v[N];

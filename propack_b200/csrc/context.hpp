@@ -65,6 +65,8 @@ class Context {
   }
   // set by Comm-aware code (c_api: comm_init) when peer windows are mapped
   void** peer_table = nullptr; int peer_rank = 0, peer_world = 1;
+  void** coef_table = nullptr;           // Comm::coef window bases (device array), for the fused coefficient all-reduce
+  unsigned long long coef_seq = 0;
   unsigned int* host_err = nullptr;      // pinned + mapped error word
   unsigned int* host_err_dev = nullptr;
   // Call right after launching the kernel that owns `p`.  kind: 0 = sum (dot products), 1 = sqrt(sum) (norms).

@@ -282,7 +282,6 @@ template <class T> class Engine {
         if (l <= 0) return;
         const T* blk = basis + (size_t)(pcol - 1) * ld;
         k_gemv_t<T>(c, len, l, blk, ld, vnew, hbuf.p);
-        reduce_coefficients(l);
         const bool last = (seen == count);
         k_gemv_n<T>(c, len, l, blk, ld, hbuf.p, R(1), vnew, -1, vnew, last ? &p : nullptr);
         if (last) published = true;
@@ -300,12 +299,8 @@ template <class T> class Engine {
     k_zero<T>(c, len, vnew);
     c.ctr.nreorth += 1;
   }
-  // row-sharded run: all-reduce of the l coefficients h = V_local^H q_local (the OpenMP build's CRITICAL
-  // sum over threads, dreorth.F:177-197)
-  void reduce_coefficients(int l) {
-    if (!dist) return;
-    Comm::get().allreduce_sum(reinterpret_cast<R*>(hbuf.p), (size_t)l * (scalar_traits<T>::is_complex ? 2 : 1), c.stream);
-  }
+  // (row-sharded run: the all-reduce of the l coefficients h = V_local^H q_local -- the OpenMP build's CRITICAL sum over
+  // threads, dreorth.F:177-197 -- happens inside k_gemv_t: fused into its finalize kernel over NVLink peer memory, or NCCL.)
 
   // --- dgetu0 (dgetu0.F:11-89) ---------------------------------------------------------------------------
   // u0 <- op(A) r, r ~ LAPACK uniform(-1,1) stream from iseed (1,3,5,7) (reset on every call), then

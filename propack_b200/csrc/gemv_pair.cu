@@ -19,6 +19,7 @@
 //                    fused ||out||^2 -> last-CTA publication (dreorth's pdnrm2 for free)
 #include <algorithm>
 
+#include "comm.hpp"
 #include "kernels.cuh"
 
 namespace pb {
@@ -144,6 +145,61 @@ gemv_t_finalize(int l, int G, const T* __restrict__ part, int lpad, T* __restric
   }
 }
 
+// Row-sharded run with mapped peers: the finalize kernel also performs the cross-rank all-reduce of the l coefficients
+// (the OpenMP build's CRITICAL sum over threads, dreorth.F:177-197, across GPUs).  Every CTA pushes its 32 local sums into
+// every rank's coefficient window over NVLink; the last CTA raises this rank's flag everywhere, waits for all ranks'
+// flags in its own window and sums the P contributions in rank order (identical on every rank) into h.
+template <class T>
+__global__ void __launch_bounds__(kThreads)
+gemv_t_finalize_fused(int l, int G, const T* __restrict__ part, int lpad, T* __restrict__ h, void** bases, int rank, int world,
+                      int buf, unsigned long long seq, unsigned int* ticket, volatile unsigned int* host_err) {
+  __shared__ T sm[8][33];
+  __shared__ bool is_last;
+  constexpr size_t kBuf = (size_t)Comm::kMaxRanks * Comm::kCoefMax * 16;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + lane;
+  T s = zero_<T>();
+  if (c < l)
+    for (int g = w; g < G; g += 8) s = s + part[(long)g * lpad + c];
+  sm[w][lane] = s;
+  __syncthreads();
+  if (w == 0 && c < l) {
+    T t = sm[0][lane];
+#pragma unroll
+    for (int ww = 1; ww < 8; ++ww) t = t + sm[ww][lane];
+    for (int r = 0; r < world; ++r) {
+      T* dst = reinterpret_cast<T*>(static_cast<char*>(bases[r]) + (size_t)buf * kBuf + ((size_t)rank * Comm::kCoefMax) * 16);
+      dst[c] = t;
+    }
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) is_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (!is_last) return;
+  if ((int)threadIdx.x < world) {
+    unsigned long long* f = reinterpret_cast<unsigned long long*>(static_cast<char*>(bases[threadIdx.x]) + 2 * kBuf);
+    *reinterpret_cast<volatile unsigned long long*>(f + buf * Comm::kMaxRanks + rank) = seq;
+    const unsigned long long* mine = reinterpret_cast<const unsigned long long*>(static_cast<char*>(bases[rank]) + 2 * kBuf);
+    const long long t0 = clock64();
+    while (*reinterpret_cast<const volatile unsigned long long*>(mine + buf * Comm::kMaxRanks + threadIdx.x) != seq) {
+      if (clock64() - t0 > 20000000000LL) { *host_err = 1u; break; }   // ~10 s: a peer died; do not hang the GPU
+    }
+  }
+  __syncthreads();
+  __threadfence();
+  const char* my = static_cast<const char*>(bases[rank]) + (size_t)buf * kBuf;
+  for (int cc = threadIdx.x; cc < l; cc += kThreads) {
+    T t = zero_<T>();
+    for (int q = 0; q < world; ++q) {
+      const volatile T* src = reinterpret_cast<const volatile T*>(my + ((size_t)q * Comm::kCoefMax) * 16);
+      t = t + ld_volatile(src + cc);
+    }
+    h[cc] = t;
+  }
+  if (threadIdx.x == 0) *ticket = 0u;
+}
+
 template <class T, bool SUB>
 __global__ void __launch_bounds__(kThreads, 2)
 gemv_n_kernel(long L, int l, const T* __restrict__ V, long ldv, const T* __restrict__ h, real_t<T> cin,
@@ -247,8 +303,18 @@ template <class T> void k_gemv_t(Context& c, long L, int l, const T* V, long ldv
   }
   gemv_t_kernel<T><<<dim3(gx, nchunks), kThreads, smem, c.stream>>>(L, l, V, ldv, q, part, lpad);
   PB_LAUNCH_CHECK();
-  gemv_t_finalize<T><<<ceil_div(l, 32), kThreads, 0, c.stream>>>(l, gx, part, lpad, h);
-  PB_LAUNCH_CHECK();
+  if (c.dist_reduce && c.coef_table != nullptr && l <= Comm::kCoefMax) {
+    // fused: finalize + cross-rank all-reduce of the coefficients over NVLink peer memory, one launch
+    c.coef_seq += 1;
+    gemv_t_finalize_fused<T><<<ceil_div(l, 32), kThreads, 0, c.stream>>>(l, gx, part, lpad, h, c.coef_table, c.peer_rank, c.peer_world,
+                                                                         (int)(c.coef_seq & 1ull), c.coef_seq, c.ticket, c.host_err_dev);
+    PB_LAUNCH_CHECK();
+  } else {
+    gemv_t_finalize<T><<<ceil_div(l, 32), kThreads, 0, c.stream>>>(l, gx, part, lpad, h);
+    PB_LAUNCH_CHECK();
+    if (c.dist_reduce)
+      Comm::get().allreduce_sum(reinterpret_cast<real_t<T>*>(h), (size_t)l * (scalar_traits<T>::is_complex ? 2 : 1), c.stream);
+  }
   c.ctr.launches += 2;
 }
 
