@@ -64,8 +64,8 @@ class DenseSpec:
         self.shape, self.table, self.dtype, self.nnz = (m, n), table, np.dtype(np.float64), m * n
 
     def replica(self, rows):
-        from propack_b200 import synth
-        return synth.dense_planted(self.shape[0], self.shape[1], DENSE_SEED, self.table, rows=np.arange(rows))
+        from oracle import synth_ref
+        return synth_ref.dense_planted(self.shape[0], self.shape[1], DENSE_SEED, self.table, rows=np.arange(rows))
 
 
 def make_operator(A):

@@ -255,6 +255,7 @@ int propack_b200_solver_local_rows(int solver, int* m_local, int* n_local, long*
 int propack_b200_init(void);                         /* create the context on the current device; 0 or negative */
 int propack_b200_set_stream(void* cuda_stream);      /* run on a caller stream (e.g. torch's current stream) */
 int propack_b200_set_lapack(const char* path);       /* shared object providing {d,s}bdsqr / {d,s}bdsdc */
+int propack_b200_set_option(const char* name, int value); /* "l2_persist": keep the SpMV's gathered vector L2-resident (default 0: measured slower on config 5) */
 void propack_b200_set_profile(int on);               /* per-phase CUDA-event timers (adds synchronisation) */
 void propack_b200_reset_counters(void);
 /* out[0..15] = nopx nreorth ndot nitref nrestart nbsvd nlandim nsing nsteps reorth_passes reorth_cols

@@ -792,6 +792,14 @@ int propack_b200_set_lapack(const char* path) {
   return 0;
   PB_API_CATCH(return code__)
 }
+int propack_b200_set_option(const char* name, int value) {
+  PB_API_TRY
+  Context& c = Context::get();
+  const std::string n = name ? name : "";
+  if (n == "l2_persist") { c.l2_persist = value != 0; c.set_l2_window(nullptr, 0); return 0; }
+  throw std::runtime_error("propack_b200: unknown option '" + n + "'");
+  PB_API_CATCH(return code__)
+}
 void propack_b200_set_profile(int on) { try { Context::get().profile = on != 0; } catch (...) {} }
 void propack_b200_reset_counters(void) { try { Context::get().ctr = Counters(); } catch (...) {} }
 void propack_b200_get_counters(long long* out) {

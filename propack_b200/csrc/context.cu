@@ -29,6 +29,10 @@ Context::Context() {
     throw CudaError(cudaErrorInvalidDevice, buf);
   }
   PB_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+  l2_persist_max = (size_t)prop.persistingL2CacheMaxSize;
+  l2_window_max = (size_t)prop.accessPolicyMaxWindowSize;
+  if (l2_persist_max > 0) cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, l2_persist_max);
+  if (const char* e = std::getenv("PROPACK_B200_L2_PERSIST")) l2_persist = e[0] != '0';
   PB_CUDA(cudaHostAlloc((void**)&host_slots, sizeof(ScalarSlot) * kSlots, cudaHostAllocMapped));
   std::memset((void*)host_slots, 0, sizeof(ScalarSlot) * kSlots);
   PB_CUDA(cudaHostGetDevicePointer((void**)&host_slots_dev, (void*)host_slots, 0));
@@ -44,11 +48,34 @@ Context::Context() {
   profile = std::getenv("PROPACK_B200_PROFILE") != nullptr;
 }
 
+void Context::set_l2_window(const void* p, size_t bytes) {
+  if (!l2_persist || l2_persist_max == 0 || bytes < (16u << 20)) {
+    if (l2_win_ptr) {   // drop a stale window
+      cudaStreamAttrValue a{};
+      a.accessPolicyWindow.num_bytes = 0;
+      cudaStreamSetAttribute(stream, cudaStreamAttributeAccessPolicyWindow, &a);
+      l2_win_ptr = nullptr; l2_win_bytes = 0;
+    }
+    return;
+  }
+  if (p == l2_win_ptr && bytes == l2_win_bytes) return;
+  cudaStreamAttrValue a{};
+  const size_t nb = bytes < l2_window_max ? bytes : l2_window_max;
+  a.accessPolicyWindow.base_ptr = const_cast<void*>(p);
+  a.accessPolicyWindow.num_bytes = nb;
+  a.accessPolicyWindow.hitRatio = nb <= l2_persist_max ? 1.0f : (float)((double)l2_persist_max / (double)nb);
+  a.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+  a.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+  PB_CUDA(cudaStreamSetAttribute(stream, cudaStreamAttributeAccessPolicyWindow, &a));
+  l2_win_ptr = p; l2_win_bytes = bytes;
+}
+
 void Context::set_stream(cudaStream_t s) {
   PB_CUDA(cudaStreamSynchronize(stream));
   if (owns_stream && stream) cudaStreamDestroy(stream);
   stream = s;
   owns_stream = false;
+  l2_win_ptr = nullptr; l2_win_bytes = 0;
 }
 
 double Context::wait(const Pending& p, double* imag) {

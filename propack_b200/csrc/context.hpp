@@ -76,6 +76,14 @@ class Context {
   // Spin until the kernel that owns `p` has published; returns the real part (imag via out param).
   double wait(const Pending& p, double* imag = nullptr);
 
+  // Optional L2 residency hint for the vector a gather-SpMV reads at random (x): an access-policy window with the
+  // "persisting" hit property.  Measured on config 5 (x = 80 MB): 832 us with the window vs 763 us without -- the
+  // set-aside hurts the streamed operands more than it helps x -- so it is OFF by default (PROPACK_B200_L2_PERSIST=1 or
+  // propack_b200_set_option("l2_persist", 1) to experiment).
+  bool l2_persist = false;
+  size_t l2_persist_max = 0, l2_window_max = 0;
+  const void* l2_win_ptr = nullptr; size_t l2_win_bytes = 0;
+  void set_l2_window(const void* p, size_t bytes);
   void set_stream(cudaStream_t s);
   void sync() { PB_CUDA(cudaStreamSynchronize(stream)); }
   int grid_for(long work_items, int per_cta, int ctas_per_sm) const {

@@ -189,6 +189,7 @@ void k_spmv(Context& c, const CsrDevice<T>& A, bool conj, const T* x, T* y, real
     attr_set = true;
   }
   const bool cj = conj && scalar_traits<T>::is_complex;
+  c.set_l2_window(x, sizeof(T) * (size_t)A.cols);   // keep the gathered vector L2-resident while (ci, va) stream through
   if (A.n_long > 0) {
     if (cj) spmv_long_kernel<T, true><<<A.n_long, kLongThreads, 0, c.stream>>>(A, x, y, coef, prev);
     else spmv_long_kernel<T, false><<<A.n_long, kLongThreads, 0, c.stream>>>(A, x, y, coef, prev);

@@ -303,7 +303,8 @@ def test_dense_synthetic_generator_bit_exact_and_irl(oracle):
     from propack_b200 import f77, synth
     m, n, seed = 3001, 200, 7
     T = synth.planted_table(synth.planted_coefficients(m, n))
-    A = synth.dense_planted(m, n, seed, T)
+    from oracle import synth_ref
+    A = synth_ref.dense_planted(m, n, seed, T)
     op = synth.device_dense_planted(m, n, seed, T)
     for j in (0, 1, 63, 64, 199):
         e = np.zeros(n); e[j] = 1.0

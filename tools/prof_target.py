@@ -20,10 +20,15 @@ L.propack_b200_bench_gemm_d.argtypes = [C.c_long, C.c_int, C.c_int, C.c_int]
 m = A.shape[0]
 out = {}
 REPS = int(os.environ.get("PROF_REPS", "3"))   # ncu captures: PROF_REPS=1 keeps the launch count small
-for adj in (0, 1):
-    t = L.propack_b200_bench_spmv(C.c_int(op.handle), C.c_int(adj), C.c_int(REPS), C.c_int(1))
-    out[f"spmv_{adj}_ms"] = t
-    out[f"spmv_{adj}_gbs"] = (op.bytes_per_product(bool(adj)) + 8.0 * m) / t / 1e6
+for persist in ((1, 0) if os.environ.get("PROF_L2_AB") else (1,)):
+    L.propack_b200_set_option(b"l2_persist", C.c_int(persist))
+    for adj in (0, 1):
+        for flush in ((1, 0) if os.environ.get("PROF_L2_AB") else (1,)):
+            t = L.propack_b200_bench_spmv(C.c_int(op.handle), C.c_int(adj), C.c_int(REPS), C.c_int(flush))
+            tag = f"spmv_{adj}" + ("" if persist else "_nopersist") + ("" if flush else "_noflush")
+            out[tag + "_ms"] = t
+            out[tag + "_gbs"] = (op.bytes_per_product(bool(adj)) + 8.0 * m) / t / 1e6
+L.propack_b200_set_option(b"l2_persist", C.c_int(1))
 for l in (16, 64, 256):
     t = L.propack_b200_bench_reorth_d(m, l, REPS, 1)
     out[f"reorth_l{l}_ms"] = t
