@@ -351,3 +351,16 @@ def test_c2_full_size_parity_and_properties(oracle):
     assert np.max(np.abs(U.T @ U - np.eye(k))) < 1e-6 and np.max(np.abs(V.T @ V - np.eye(k))) < 1e-6
     ref = oracle.lansvd(A, k, kmax, tol=tol, u0=u0, cgs=True, jobu=False, jobv=False)
     assert ref["k"] == k and relerr(S, ref["sigma"]) < 1e-10
+
+
+@pytest.mark.gpu
+def test_example_driver_on_illc1850_rra():
+    """BASELINE configs[0]: the reference's example program (example.F on illc1850.rra, k = 10, DLANSVD) end to end:
+    Harwell-Boeing file in, singular values compared with the stored reference values as `compare` does."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    p = subprocess.run([sys.executable, os.path.join(root, "examples", "example.py"), os.path.join(GOLDEN, "illc1850.rra"), "--k", "10",
+                        "--kmax", "100", "--compare", os.path.join(GOLDEN, "Sigma_illc1850.ascii")], capture_output=True, text=True, timeout=600)
+    sys.stdout.write(p.stdout[-3000:]); sys.stderr.write(p.stderr[-2000:])
+    assert p.returncode == 0 and "max relative error of sigma" in p.stdout
