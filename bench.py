@@ -531,6 +531,12 @@ def run_ours_sharded(args):
     t = torch.tensor([float(np.sum(times))], device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX)
     total_ms = float(t.item())
     value = steps / (total_ms * 1e-3)          # every rank executes the same Lanczos steps: count them once
+    # per-phase CUDA-event timers of one extra solve (rank 0's view; adds an event sync per phase, so it is slower than the
+    # timed solves; "aprod" includes the wait for the other ranks' slices, "level1" the fused normalise + all-gather push)
+    propack_b200.set_profile(True)
+    pms, _, _, _, _ = solve_resident()
+    ph = {kname: v["ms"] for kname, v in propack_b200.phase_ms().items()}
+    propack_b200.set_profile(False)
 
     # e2e: this rank's shard from pinned host memory -> device, solve, its slices of U, V and sigma back to the host
     rows, colt = pdist.shard_csr(A, world, rank)
@@ -586,7 +592,7 @@ def run_ours_sharded(args):
                     "time_to_k_triplets_s": float(np.mean(e2e_t)),
                     "path": "per rank: propack_b200_csr_create_sharded_d (pinned host shard) + solver session + local U,V slices and "
                             "sigma copied back; bytes are per rank"},
-            "roofline": None, "clocks": clk,
+            "roofline": None, "phases_ms_profiled_solve": ph, "profiled_solve_ms": pms, "clocks": clk,
         }
         sys.stdout.flush()
         os.dup2(saved_stdout, 1)

@@ -13,9 +13,9 @@
 //   - A fragments: one LDG.64 per lane per k-step straight from HBM (8 consecutive rows x 4
 //     columns = four 64-byte segments, every 32-byte sector fully used), prefetched one K chunk
 //     ahead; the tall operand has no reuse across warps, so it is not staged in shared memory.
-//   - W is pre-packed on the host in DMMA B-fragment order (pack_w below); the CTA stages one
-//     K chunk of it in shared memory (conflict-free 256-byte rows) and all 8 warps x MT m-tiles
-//     reuse it, so W traffic from L2 is |W| per 64*MT rows instead of per 8 rows.
+//   - W is pre-packed on the host in DMMA B-fragment order (pack_w below); the CTA double-buffers
+//     K chunks of it in shared memory with cp.async (conflict-free 256-byte rows) and all 8 warps x MT
+//     m-tiles reuse it, so W traffic from L2 is |W| per 64*MT rows instead of per 8 rows.
 //   - N > 128 (more accumulators than registers): column slabs of 128 go through a scratch panel
 //     and are copied over A after the last slab.
 //   - float / complex-float bases are widened to FP64 on load (same kernel, half the bytes).
@@ -36,20 +36,39 @@ __device__ inline void dmma(double& c0, double& c1, double a, double b) {
 }
 
 // NT = n-tiles (8 columns each) and MT = m-tiles (8 rows each) held in DMMA accumulators by one warp.
-// The CTA (8 warps) owns 64*MT consecutive rows; all warps walk K in lock step, KS k-steps (4 columns
-// each) at a time, sharing one shared-memory copy of the packed W chunk; A fragments for the next
-// chunk are prefetched from HBM into registers while the current chunk is multiplied.
-constexpr int GK_KS = 4;
+// The CTA (8 warps) owns 64*MT consecutive rows; all warps walk K in lock step, GK_KS k-steps (4 columns each) at a
+// time.  The packed W chunk is double-buffered in shared memory with cp.async (one barrier per chunk: wait for chunk
+// ch, barrier, start the copy of chunk ch+1 into the buffer everybody just finished reading, multiply chunk ch), and
+// the A fragments of chunk ch+1 are prefetched from HBM into registers while chunk ch is multiplied.
+constexpr int GK_KS_MAX = 8;                                        // pack_w pads W to whole chunks of this many k-steps
+template <int MT> constexpr int gk_ks() { return MT >= 2 ? 4 : 8; }  // k-steps per chunk: 2*KS*MT A registers per lane
+__device__ inline void cp_async16(void* smem_dst, const void* gmem_src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src));
+}
+__device__ inline void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ inline void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 template <class R, int NT, int MT>
 __global__ void __launch_bounds__(kThreads)
 gemm_tall_kernel(long Mr, int N, int K, R* A, long lda, const double* __restrict__ Wp, int nt_total, int nt0,
                  R* dst, long ldd) {
-  __shared__ __align__(16) double wsm[GK_KS * NT * 32];
+  extern __shared__ __align__(16) double wsm[];   // [2][GK_KS * NT * 32]
+  constexpr int GK_KS = gk_ks<MT>();
+  constexpr int CHUNK = GK_KS * NT * 32;          // doubles per W chunk
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int kk = lane & 3, rr = lane >> 2;
   const int ksteps = (K + 3) / 4;
-  const int nchunks = (ksteps + GK_KS - 1) / GK_KS;
+  const int nchunks = (ksteps + GK_KS - 1) / GK_KS;   // Wp is zero-padded to nchunks*GK_KS k-steps (pack_w)
   const long tile_rows = 64L * MT;
+  // W chunk ch -> buffer b: per k-step a contiguous run of NT*32 doubles (tiles nt0 .. nt0+NT-1), 16-byte pieces
+  auto stage_w = [&](int ch, int b) {
+    double* dstw = wsm + b * CHUNK;
+    for (int i = threadIdx.x; i < CHUNK / 2; i += kThreads) {
+      const int s = i / (NT * 16), rem = i - s * (NT * 16);
+      cp_async16(dstw + s * NT * 32 + rem * 2, Wp + ((long)(ch * GK_KS + s) * nt_total + nt0) * 32 + rem * 2);
+    }
+    cp_async_commit();
+  };
   for (long t0 = (long)blockIdx.x * tile_rows; t0 < Mr; t0 += (long)gridDim.x * tile_rows) {
     long row[MT];
     bool rok[MT];
@@ -69,26 +88,19 @@ gemm_tall_kernel(long Mr, int N, int K, R* A, long lda, const double* __restrict
         for (int mt = 0; mt < MT; ++mt) a[s][mt] = (rok[mt] && k < K) ? (double)A[(long)k * lda + row[mt]] : 0.0;
       }
     };
+    __syncthreads();            // the previous row tile's last chunk is fully consumed before buffer 0 is refilled
+    stage_w(0, 0);
     load_a(0, a_cur);
     for (int ch = 0; ch < nchunks; ++ch) {
-      __syncthreads();  // previous chunk's W fully consumed
-      {
-        const int s_lo = ch * GK_KS;
-        for (int i = threadIdx.x; i < GK_KS * NT * 32; i += kThreads) {
-          const int s = i / (NT * 32), rem = i - s * (NT * 32);
-          const int j = rem >> 5, l = rem & 31;
-          double v = 0.0;
-          if (s_lo + s < ksteps) v = __ldg(Wp + ((long)(s_lo + s) * nt_total + nt0 + j) * 32 + l);
-          wsm[i] = v;
-        }
-      }
-      if (ch + 1 < nchunks) load_a(ch + 1, a_nxt);
-      __syncthreads();
+      cp_async_wait<0>();       // this thread's pieces of chunk ch have landed ...
+      __syncthreads();          // ... and everybody's; also: everybody is done reading the other buffer (chunk ch-1)
+      if (ch + 1 < nchunks) { stage_w(ch + 1, (ch + 1) & 1); load_a(ch + 1, a_nxt); }
+      const double* wb = wsm + (ch & 1) * CHUNK;
 #pragma unroll
       for (int s = 0; s < GK_KS; ++s)
 #pragma unroll
         for (int j = 0; j < NT; ++j) {
-          const double b = wsm[(s * NT + j) * 32 + lane];
+          const double b = wb[(s * NT + j) * 32 + lane];
 #pragma unroll
           for (int mt = 0; mt < MT; ++mt) dmma(c[mt][j][0], c[mt][j][1], a_cur[s][mt], b);
         }
@@ -123,7 +135,13 @@ copy_cols_kernel(long Mr, int N, const R* __restrict__ src, long lds, R* __restr
 template <class R, int NT, int MT>
 void launch_slab(Context& c, long Mr, int N, int K, R* A, long lda, const double* Wp, int nt_total, int nt0, R* dst, long ldd) {
   const int grid = c.grid_for(Mr, 64 * MT, 2);
-  gemm_tall_kernel<R, NT, MT><<<grid, kThreads, 0, c.stream>>>(Mr, N, K, A, lda, Wp, nt_total, nt0, dst, ldd);
+  constexpr size_t smem = sizeof(double) * 2 * gk_ks<MT>() * NT * 32;
+  static bool attr_set = false;
+  if (!attr_set) {
+    PB_CUDA(cudaFuncSetAttribute(gemm_tall_kernel<R, NT, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  gemm_tall_kernel<R, NT, MT><<<grid, kThreads, smem, c.stream>>>(Mr, N, K, A, lda, Wp, nt_total, nt0, dst, ldd);
   PB_LAUNCH_CHECK();
   c.ctr.launches += 1;
 }
@@ -167,7 +185,8 @@ template <class R> void gemm_real(Context& c, long Mr, int N, int K, R* A, long 
 // B-fragment order: Wp[s][j][t] = W[4s + t%4][8j + t/4], zero padded.
 template <class R> std::vector<double> pack_w(int K, int N, const R* W, int ldw, int* nt_total) {
   const int ksteps = (K + 3) / 4, nt = (N + 7) / 8;
-  std::vector<double> out((size_t)ksteps * nt * 32, 0.0);
+  const int ksteps_pad = (ksteps + GK_KS_MAX - 1) / GK_KS_MAX * GK_KS_MAX;   // whole chunks: the kernel copies them unconditionally
+  std::vector<double> out((size_t)ksteps_pad * nt * 32, 0.0);
   for (int s = 0; s < ksteps; ++s)
     for (int j = 0; j < nt; ++j)
       for (int t = 0; t < 32; ++t) {
