@@ -545,7 +545,7 @@ def run_ours_sharded(args):
             pin(colt.indptr, np.int32), pin(colt.indices, np.int32), pin(colt.data, np.float64))
     sv.close(); op.close()
     e2e_t, e2e_steps = [], 0
-    for i in range(1 + max(1, min(args.steps, 3))):
+    for i in range(0 if args.no_e2e else 1 + max(1, min(args.steps, 3))):
         barrier()
         t0 = time.perf_counter()
         h = _lib.check(L.propack_b200_csr_create_sharded_d(C.c_int(m), C.c_int(n), *[a.ctypes.data_as(C.c_void_p) for a in harr], C.c_int(0)),
@@ -566,10 +566,11 @@ def run_ours_sharded(args):
         if i >= 1:
             e2e_t.append(dt); e2e_steps += propack_b200.counters()["nsteps"]
         sv2.close(); op2.close()
-    te = torch.tensor([float(np.sum(e2e_t))], device="cuda"); dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    te = torch.tensor([float(np.sum(e2e_t)) if e2e_t else 1.0], device="cuda"); dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_val = e2e_steps / float(te.item())
-    h2d = sum(a.nbytes for a in harr) + (op2.rows[1] - op2.rows[0]) * 8
-    d2h = ((op2.rows[1] - op2.rows[0]) + (op2.cols[1] - op2.cols[0])) * k * 8 + 2 * k * 8
+    rows_b, cols_b = pdist.shard_bounds(m, world, rank), pdist.shard_bounds(n, world, rank)
+    h2d = sum(a.nbytes for a in harr) + (rows_b[1] - rows_b[0]) * 8
+    d2h = ((rows_b[1] - rows_b[0]) + (cols_b[1] - cols_b[0])) * k * 8 + 2 * k * 8
     nar, nag, agb = C.c_longlong(0), C.c_longlong(0), C.c_double(0)
     L.propack_b200_comm_stats(C.byref(nar), C.byref(nag), C.byref(agb))
     if rank == 0:
@@ -589,7 +590,7 @@ def run_ours_sharded(args):
             "gpu_launches": int(launches), "host_syncs_per_solve": ctr["host_syncs"],
             "collectives_total": {"allreduce": nar.value, "allgather": nag.value, "allgather_gbytes": agb.value / 1e9},
             "e2e": {"value": e2e_val, "unit": "steps/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "time_to_k_triplets_s": float(np.mean(e2e_t)),
+                    "time_to_k_triplets_s": float(np.mean(e2e_t)) if e2e_t else None,
                     "path": "per rank: propack_b200_csr_create_sharded_d (pinned host shard) + solver session + local U,V slices and "
                             "sigma copied back; bytes are per rank"},
             "roofline": None, "phases_ms_profiled_solve": ph, "profiled_solve_ms": pms, "clocks": clk,
@@ -610,6 +611,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="(sharded arm, experiments only) skip the end-to-end leg")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -146,30 +146,82 @@ int csr_create_sharded(int mg, int ng, const int* row_rp, const int* row_ci, con
   op->m = ml; op->n = nl; op->mg = mg; op->ng = ng; op->m_off = r0; op->n_off = c0;
   op->ld_m = shard_slice(mg, cm.world); op->ld_n = shard_slice(ng, cm.world);
   op->sharded = true;
-  auto upload = [&](int rows, long width, const int* rp_in, const int* ci_in, const T* va_in, DeviceBuffer<int>& rp, DeviceBuffer<int>& ci,
-                    DeviceBuffer<T>& va, CsrDevice<T>& D, long cols_padded, DeviceBuffer<int>& lr) {
-    std::vector<int> hrp(rows + 1);
-    for (int i = 0; i <= rows; ++i) hrp[i] = rp_in[i] - base;
-    if (hrp[0] != 0) throw std::runtime_error("propack_b200: sharded CSR row pointers must start at the index base");
-    const long nnz = hrp[rows];
+  // number of column groups (sub-SpMVs per product), must divide world; 1 unless PROPACK_B200_SPMV_GROUPS says
+  // otherwise (the grouped, chunk-pipelined product is an experiment that measured slower: see ShardedCsrOperator)
+  int G = 1;
+  if (const char* e = std::getenv("PROPACK_B200_SPMV_GROUPS")) G = std::max(1, std::atoi(e));
+  G = std::min(G, cm.world);
+  while (cm.world % G) --G;
+  auto upload = [&](int d, int rows, long width, long ld, const int* rp_in, const int* ci_in, const T* va_in) {
+    const long nnz = (long)rp_in[rows] - rp_in[0];
+    if (rp_in[0] != base) throw std::runtime_error("propack_b200: sharded CSR row pointers must start at the index base");
+    const int P = cm.world, per = P / G;
+    auto group_of = [&](int col) {   // ring distance of the owner of `col` behind this rank -> group
+      const int owner = (int)(col / ld);
+      const int dist = ((cm.rank - owner) % P + P) % P;
+      return dist / per;
+    };
+    // pass 1: validate, count per (group, row)
+    std::vector<std::vector<int>> grp(G, std::vector<int>((size_t)rows + 1, 0));
+    for (int i = 0; i < rows; ++i) {
+      int prevc = -1;
+      for (long p = rp_in[i] - base; p < rp_in[i + 1] - base; ++p) {
+        const int col = ci_in[p] - base;
+        if (col < 0 || col >= width) throw std::runtime_error("propack_b200: sharded CSR index out of range");
+        if (col < prevc) throw std::runtime_error("propack_b200: CSR indices must be sorted within each row");
+        prevc = col;
+        grp[group_of(col)][i + 1] += 1;
+      }
+    }
+    std::vector<long> goff(G + 1, 0);
+    for (int g = 0; g < G; ++g) {
+      for (int i = 0; i < rows; ++i) grp[g][i + 1] += grp[g][i];
+      goff[g + 1] = goff[g] + grp[g][rows];
+    }
+    // pass 2: scatter into the group-major arrays (columns stay ascending inside a row)
     std::vector<int> hci(std::max<long>(nnz, 1));
-    for (long p = 0; p < nnz; ++p) {
-      hci[p] = ci_in[p] - base;
-      if (hci[p] < 0 || hci[p] >= width) throw std::runtime_error("propack_b200: sharded CSR index out of range");
-    }
+    std::vector<T> hva(std::max<long>(nnz, 1));
+    std::vector<std::vector<int>> next(G);
+    for (int g = 0; g < G; ++g) next[g].assign(grp[g].begin(), grp[g].end() - 1);
     for (int i = 0; i < rows; ++i)
-      for (int p = hrp[i] + 1; p < hrp[i + 1]; ++p)
-        if (hci[p - 1] > hci[p]) throw std::runtime_error("propack_b200: CSR indices must be sorted within each row");
-    rp.alloc(rows + 1); ci.alloc(std::max<long>(nnz, 1)); va.alloc(std::max<long>(nnz, 1));
-    PB_CUDA(cudaMemcpy(rp.p, hrp.data(), sizeof(int) * (rows + 1), cudaMemcpyHostToDevice));
-    if (nnz) {
-      PB_CUDA(cudaMemcpy(ci.p, hci.data(), sizeof(int) * nnz, cudaMemcpyHostToDevice));
-      PB_CUDA(cudaMemcpy(va.p, va_in, sizeof(T) * nnz, cudaMemcpyHostToDevice));
+      for (long p = rp_in[i] - base; p < rp_in[i + 1] - base; ++p) {
+        const int col = ci_in[p] - base, g = group_of(col);
+        const long q = goff[g] + next[g][i]++;
+        hci[q] = col; hva[q] = va_in[p];
+      }
+    std::vector<int> hrp((size_t)G * (rows + 1)), hlong;
+    std::vector<int> long_off(G + 1, 0);
+    for (int g = 0; g < G; ++g) {
+      std::copy(grp[g].begin(), grp[g].end(), hrp.begin() + (size_t)g * (rows + 1));
+      const std::vector<int> lr = csr_long_rows(grp[g].data(), rows, spmv_group_nnz<T>());
+      hlong.insert(hlong.end(), lr.begin(), lr.end());
+      long_off[g + 1] = (int)hlong.size();
     }
-    fill_device_csr<T>(D, rows, (int)cols_padded, nnz, rp, ci, va, hrp.data(), 0, lr);
+    op->rp_all[d].alloc(hrp.size()); op->ci_all[d].alloc(hci.size()); op->va_all[d].alloc(hva.size());
+    op->long_all[d].alloc(std::max<size_t>(hlong.size(), 1));
+    PB_CUDA(cudaMemcpy(op->rp_all[d].p, hrp.data(), sizeof(int) * hrp.size(), cudaMemcpyHostToDevice));
+    PB_CUDA(cudaMemcpy(op->ci_all[d].p, hci.data(), sizeof(int) * hci.size(), cudaMemcpyHostToDevice));
+    PB_CUDA(cudaMemcpy(op->va_all[d].p, hva.data(), sizeof(T) * hva.size(), cudaMemcpyHostToDevice));
+    if (!hlong.empty()) PB_CUDA(cudaMemcpy(op->long_all[d].p, hlong.data(), sizeof(int) * hlong.size(), cudaMemcpyHostToDevice));
+    op->groups[d].resize(G);
+    for (int g = 0; g < G; ++g) {
+      auto& Gr = op->groups[d][g];
+      Gr.M.rows = rows; Gr.M.cols = (int)(ld * P); Gr.M.nnz = goff[g + 1] - goff[g];
+      Gr.M.rp = op->rp_all[d].p + (size_t)g * (rows + 1);
+      Gr.M.ci = op->ci_all[d].p + goff[g];
+      Gr.M.va = op->va_all[d].p + goff[g];
+      Gr.M.lpr_log2 = csr_lanes_per_row_log2(Gr.M.nnz, rows, spmv_group_nnz<T>());
+      Gr.M.n_long = long_off[g + 1] - long_off[g];
+      Gr.M.long_rows = Gr.M.n_long ? op->long_all[d].p + long_off[g] : nullptr;
+      Gr.src_mask = 0;
+      for (int k = g * per; k < (g + 1) * per; ++k) {
+        const int src = ((cm.rank - k) % P + P) % P;
+        if (src != cm.rank) Gr.src_mask |= 1u << src;
+      }
+    }
   };
-  upload(ml, ng, row_rp, row_ci, row_va, op->rp, op->ci, op->va, op->A, op->ld_n * cm.world, op->lrows);
-  upload(nl, mg, colt_rp, colt_ci, colt_va, op->trp, op->tci, op->tva, op->At, op->ld_m * cm.world, op->tlrows);
+  upload(0, ml, ng, op->ld_n, row_rp, row_ci, row_va);
+  upload(1, nl, mg, op->ld_m, colt_rp, colt_ci, colt_va);
   op->alloc_gather_buffers();
   OpEntry e; e.tag = abi<T>::tag; e.kind = 2; e.op = op;
   const int h = g_next_op++;

@@ -29,6 +29,8 @@ Context::Context() {
     throw CudaError(cudaErrorInvalidDevice, buf);
   }
   PB_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+  PB_CUDA(cudaStreamCreateWithFlags(&stream2, cudaStreamNonBlocking));
+  PB_CUDA(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
   l2_persist_max = (size_t)prop.persistingL2CacheMaxSize;
   l2_window_max = (size_t)prop.accessPolicyMaxWindowSize;
   if (l2_persist_max > 0) cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, l2_persist_max);
@@ -44,6 +46,8 @@ Context::Context() {
   PB_CUDA(cudaMalloc((void**)&partials, sizeof(double) * 2 * kMaxCtas));
   PB_CUDA(cudaMalloc((void**)&ticket, sizeof(unsigned int)));
   PB_CUDA(cudaMemset(ticket, 0, sizeof(unsigned int)));
+  PB_CUDA(cudaMalloc((void**)&tickets8, sizeof(unsigned int) * 8));
+  PB_CUDA(cudaMemset(tickets8, 0, sizeof(unsigned int) * 8));
   PB_CUDA(cudaDeviceSynchronize());
   profile = std::getenv("PROPACK_B200_PROFILE") != nullptr;
 }

@@ -29,6 +29,8 @@ class Context {
  public:
   static Context& get();       // lazily created on the current device
   cudaStream_t stream = nullptr;
+  cudaStream_t stream2 = nullptr;       // side stream: the NVLink push of the chunk-pipelined sharded SpMV runs here
+  cudaEvent_t ev_fork = nullptr;        // main stream -> side stream dependency
   bool owns_stream = true;
   int device = 0;
   int num_sms = 148;
@@ -42,6 +44,7 @@ class Context {
   ScalarSlot* dev_slots = nullptr;
   double* partials = nullptr;
   unsigned int* ticket = nullptr;
+  unsigned int* tickets8 = nullptr;     // per-destination arrival counters of the staggered all-gather push
   unsigned long long seq = 0;
   int next_slot = 0;
 
@@ -85,7 +88,7 @@ class Context {
   const void* l2_win_ptr = nullptr; size_t l2_win_bytes = 0;
   void set_l2_window(const void* p, size_t bytes);
   void set_stream(cudaStream_t s);
-  void sync() { PB_CUDA(cudaStreamSynchronize(stream)); }
+  void sync() { PB_CUDA(cudaStreamSynchronize(stream)); PB_CUDA(cudaStreamSynchronize(stream2)); }
   int grid_for(long work_items, int per_cta, int ctas_per_sm) const {
     long need = (work_items + per_cta - 1) / per_cta;
     long cap = (long)num_sms * ctas_per_sm;

@@ -77,9 +77,21 @@ template <class T> struct CsrOperator : LinOp<T> {
 // gathered vector directly.
 template <class T> struct ShardedCsrOperator : LinOp<T> {
   using R = real_t<T>;
-  DeviceBuffer<int> rp, ci, trp, tci, lrows, tlrows;
-  DeviceBuffer<T> va, tva, xbuf_n, xbuf_m;
-  CsrDevice<T> A, At;  // A: m_loc x (world*ld_n);  At: n_loc x (world*ld_m)
+  // Each local operand (direction 0: rows of A for A x; direction 1: rows of (A[:, cols])^T for A^H x) is stored as G
+  // column groups (G = 1 by default: one local SpMV, every output element summed in the same order as on one GPU).
+  // G > 1 (PROPACK_B200_SPMV_GROUPS) is the chunk-pipelining experiment: group g holds the entries whose column belongs
+  // to the ranks at ring distance [g*P/G, (g+1)*P/G) behind this rank -- the order in which a staggered push delivers
+  // the slices -- and the product becomes G sub-SpMVs  y = A_g x_g + y  gated on their own slices.  Measured on config 5
+  // at 8 GPUs it LOSES (1.13 s at G=1, 1.15 / 1.25 / 1.47 s at G=2/4/8): the sub-SpMVs' shorter rows cost more than
+  // they hide, because this rank's own push runs on the same stream ahead of them; overlapping needs the push on a
+  // concurrent stream (next step).
+  struct Group {
+    CsrDevice<T> M;
+    unsigned int src_mask = 0;   // ranks whose slices this group reads (own rank excluded: no wait needed)
+  };
+  std::vector<Group> groups[2];
+  DeviceBuffer<int> rp_all[2], ci_all[2], long_all[2];
+  DeviceBuffer<T> va_all[2], xbuf[2];
   // gather buffers: [world*ld elements | kMaxRanks arrival flags]; peer windows when NVLink peer memory is mapped
   // (index 0: the n-vector gathered for A x, index 1: the m-vector gathered for A^H x)
   T* xfull[2] = {nullptr, nullptr};
@@ -96,10 +108,9 @@ template <class T> struct ShardedCsrOperator : LinOp<T> {
       const size_t bytes = sizeof(T) * (size_t)ld_of(d) * cm.world + sizeof(unsigned long long) * Comm::kMaxRanks;
       if (fused) { win[d] = cm.alloc_window(bytes); xfull[d] = static_cast<T*>(win[d].base[cm.rank]); }
       else {
-        DeviceBuffer<T>& b = d ? xbuf_m : xbuf_n;
-        b.alloc(bytes / sizeof(T) + 1);
-        PB_CUDA(cudaMemset(b.p, 0, bytes));
-        xfull[d] = b.p;
+        xbuf[d].alloc(bytes / sizeof(T) + 1);
+        PB_CUDA(cudaMemset(xbuf[d].p, 0, bytes));
+        xfull[d] = xbuf[d].p;
       }
     }
   }
@@ -114,7 +125,8 @@ template <class T> struct ShardedCsrOperator : LinOp<T> {
     const int d = adjoint ? 1 : 0;
     Comm& cm = Comm::get();
     epoch[d] += 1;
-    k_scal_push<T>(c, adjoint ? this->m : this->n, ld_of(d), x, scale, win[d].table_dev, cm.rank, cm.world, epoch[d]);
+    k_scal_push<T>(c, adjoint ? this->m : this->n, ld_of(d), x, scale, win[d].table_dev, cm.rank, cm.world, epoch[d],
+                   /*staggered=*/groups[d].size() > 1, xfull[d] + (size_t)cm.rank * ld_of(d));
     staged_ptr[d] = x; staged_valid[d] = true;
     return true;
   }
@@ -122,20 +134,24 @@ template <class T> struct ShardedCsrOperator : LinOp<T> {
   void apply(Context& c, bool adjoint, const T* x, T* y, R coef, const T* prev, Pending* nrm) override {
     Comm& cm = Comm::get();
     const int d = adjoint ? 1 : 0;
-    if (staged_valid[d] && staged_ptr[d] == x && nrm != nullptr) {
-      // the slices were pushed by the producers (stage_scaled); wait for all of them, then a purely local SpMV.
-      // (nrm != nullptr: the cross-rank norm reduction that follows is what makes reusing the buffer safe.)
-      k_wait_flags(c, flags(d), cm.world, epoch[d]);
-    } else {
-      cm.allgather(x, xfull[d], sizeof(T) * (size_t)ld_of(d), c.stream);
-    }
+    // staged: the slices are being pushed by the producers (stage_scaled); each group waits only for its own sources.
+    // (nrm != nullptr: the cross-rank norm reduction that follows is what makes reusing the buffer safe.)
+    const bool staged = staged_valid[d] && staged_ptr[d] == x && nrm != nullptr;
+    if (!staged) cm.allgather(x, xfull[d], sizeof(T) * (size_t)ld_of(d), c.stream);
     staged_valid[d] = false;
-    k_spmv<T>(c, adjoint ? At : A, /*conj=*/adjoint, xfull[d], y, coef, prev, nrm);
+    const size_t G = groups[d].size();
+    for (size_t g = 0; g < G; ++g) {
+      if (staged) k_wait_flags(c, flags(d), groups[d][g].src_mask, epoch[d]);
+      k_spmv<T>(c, groups[d][g].M, /*conj=*/adjoint, xfull[d], y, g == 0 ? coef : R(1), g == 0 ? prev : y,
+                g + 1 == G ? nrm : nullptr);
+    }
   }
   double algorithmic_bytes(bool adjoint) const override {
     const double w = sizeof(T);
-    const CsrDevice<T>& M = adjoint ? At : A;
-    return (double)M.nnz * (w + 4) + ((double)M.rows + 1) * 4 + (double)M.cols * w + (double)M.rows * w;
+    double b = 0;
+    for (const Group& g : groups[adjoint ? 1 : 0])
+      b += (double)g.M.nnz * (w + 4) + ((double)g.M.rows + 1) * 4 + (double)g.M.rows * w;
+    return b + (double)ld_of(adjoint ? 1 : 0) * Comm::get().world * w;
   }
 };
 

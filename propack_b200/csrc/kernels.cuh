@@ -26,8 +26,9 @@ template <class T> void k_zero(Context& c, long n, T* x);          // pdzero dbl
 // row-sharded run, fused normalise + all-gather: x <- a*x and the slice is pushed into every rank's gather buffer
 // (bases_dev[r], peer memory) at offset rank*ld; arrival flags sit behind the world*ld elements of each buffer
 template <class T>
-void k_scal_push(Context& c, long n, long ld, T* x, real_t<T> a, void** bases_dev, int rank, int world, unsigned long long epoch);
-void k_wait_flags(Context& c, const unsigned long long* flags, int world, unsigned long long epoch);
+void k_scal_push(Context& c, long n, long ld, T* x, real_t<T> a, void** bases_dev, int rank, int world, unsigned long long epoch,
+                 bool staggered, T* self_slice);
+void k_wait_flags(Context& c, const unsigned long long* flags, unsigned int src_mask, unsigned long long epoch);
 // x(i) <- LAPACK xLARNV(idist=2, iseed) stream element offset+i, i=0..n-1 ; publish ||x||  (dgetu0.F:69-70).
 // `offset` = global index of this rank's first element in a row-sharded run (0 on one GPU).
 template <class T> void k_larnv_nrm(Context& c, long n, T* x, const int iseed[4], Pending* nrm, long offset = 0);

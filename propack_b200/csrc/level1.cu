@@ -29,36 +29,76 @@ scal_kernel(long n, T* __restrict__ x, real_t<T> a, const ScalarSlot* slot) {
 }
 
 // Fused "normalise + all-gather" of a row-sharded run: x <- a*x, and the scaled slice is also stored into every
-// rank's gather buffer (peer memory over NVLink; bases[r] = rank r's buffer) at this rank's offset.  The last CTA
-// raises this rank's arrival flag in every buffer once all stores are visible system-wide.
-template <class T>
+// rank's gather buffer (peer memory over NVLink; bases[r] = rank r's buffer) at this rank's offset.
+// STAGGERED = false: every pack goes to all destinations at once and the last CTA raises this rank's arrival flag
+// everywhere when everything is visible system-wide (fastest: one fence/ticket round).
+// STAGGERED = true (column-grouped SpMV experiment): destinations are served one after the other in ring order
+// (rank+1, rank+2, ...) and each destination's flag is raised as soon as ITS copy is complete.
+template <class T, bool STAGGERED>
 __global__ void __launch_bounds__(kThreads)
-scal_push_kernel(long n, long ld, T* __restrict__ x, real_t<T> a, void** bases, int rank, int world, unsigned int* ticket,
+scal_push_kernel(long n, long ld, T* __restrict__ x, real_t<T> a, void** bases, int rank, int world, unsigned int* tickets,
                  unsigned long long epoch) {
   constexpr int VEC = Pack<T>::N;
   __shared__ bool is_last;
   const long np = (n + VEC - 1) / VEC;
-  for (long i = (long)blockIdx.x * kThreads + threadIdx.x; i < np; i += (long)gridDim.x * kThreads) {
-    Pack<T> p = ld_pack(x + i * VEC);
+  if (!STAGGERED) {
+    for (long i = (long)blockIdx.x * kThreads + threadIdx.x; i < np; i += (long)gridDim.x * kThreads) {
+      Pack<T> p = ld_pack(x + i * VEC);
 #pragma unroll
-    for (int e = 0; e < VEC; ++e) p.v[e] = a * p.v[e];  // padding stays 0
-    st_pack(x + i * VEC, p);
-    for (int r = 0; r < world; ++r) st_pack(static_cast<T*>(bases[r]) + (long)rank * ld + i * VEC, p);
+      for (int e = 0; e < VEC; ++e) p.v[e] = a * p.v[e];  // padding stays 0
+      st_pack(x + i * VEC, p);
+      for (int r = 0; r < world; ++r) st_pack(static_cast<T*>(bases[r]) + (long)rank * ld + i * VEC, p);
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) is_last = (atomicAdd(tickets, 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (is_last && threadIdx.x < world) {
+      unsigned long long* flags = reinterpret_cast<unsigned long long*>(static_cast<T*>(bases[threadIdx.x]) + (long)world * ld);
+      *reinterpret_cast<volatile unsigned long long*>(flags + rank) = epoch;
+      if (threadIdx.x == 0) tickets[0] = 0u;
+    }
+    return;
   }
-  __threadfence_system();
-  __syncthreads();
-  if (threadIdx.x == 0) is_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
-  __syncthreads();
-  if (is_last && threadIdx.x < world) {
-    unsigned long long* flags = reinterpret_cast<unsigned long long*>(static_cast<T*>(bases[threadIdx.x]) + (long)world * ld);
-    *reinterpret_cast<volatile unsigned long long*>(flags + rank) = epoch;
-    if (threadIdx.x == 0) *ticket = 0u;
+  // (the scaling and the local copy were done on the main stream by scal_local_kernel; this kernel runs on the side
+  // stream and only moves the slice to the peers, so it overlaps the sub-SpMVs that consume the slices)
+  for (int d = 1; d < world; ++d) {
+    const int dest = (rank + d) % world;
+    T* dst = static_cast<T*>(bases[dest]) + (long)rank * ld;
+    // every thread re-reads exactly the packs it wrote above (program order makes them visible)
+    for (long i = (long)blockIdx.x * kThreads + threadIdx.x; i < np; i += (long)gridDim.x * kThreads)
+      st_pack(dst + i * VEC, ld_pack(x + i * VEC));
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) is_last = (atomicAdd(tickets + d, 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (is_last && threadIdx.x == 0) {
+      unsigned long long* flags = reinterpret_cast<unsigned long long*>(static_cast<T*>(bases[dest]) + (long)world * ld);
+      *reinterpret_cast<volatile unsigned long long*>(flags + rank) = epoch;
+      tickets[d] = 0u;
+    }
   }
 }
 
-// Consumer side of the fused all-gather: returns once every rank's slice of epoch `epoch` has landed in this rank's buffer.
-__global__ void wait_flags_kernel(const unsigned long long* flags, int world, unsigned long long epoch, volatile unsigned int* host_err) {
-  if ((int)threadIdx.x >= world) return;
+// x <- a*x and a copy into this rank's own slice of its gather buffer (main-stream half of the staggered push)
+template <class T>
+__global__ void __launch_bounds__(kThreads)
+scal_local_kernel(long n, T* __restrict__ x, real_t<T> a, T* __restrict__ self) {
+  constexpr int VEC = Pack<T>::N;
+  const long np = (n + VEC - 1) / VEC;
+  for (long i = (long)blockIdx.x * kThreads + threadIdx.x; i < np; i += (long)gridDim.x * kThreads) {
+    Pack<T> p = ld_pack(x + i * VEC);
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) p.v[e] = a * p.v[e];
+    st_pack(x + i * VEC, p);
+    st_pack(self + i * VEC, p);
+  }
+}
+
+// Consumer side of the fused all-gather: returns once the slices of the ranks in `src_mask` (epoch `epoch`) have landed.
+__global__ void wait_flags_kernel(const unsigned long long* flags, unsigned int src_mask, unsigned long long epoch,
+                                  volatile unsigned int* host_err) {
+  if (!((src_mask >> threadIdx.x) & 1u)) return;
   const long long t0 = clock64();
   while (*reinterpret_cast<const volatile unsigned long long*>(flags + threadIdx.x) < epoch) {
     if (clock64() - t0 > 20000000000LL) { *host_err = 1u; break; }   // ~10 s: a peer died; do not hang the GPU
@@ -202,13 +242,23 @@ template <class T> void k_scal_inv_slot(Context& c, long n, T* x, const ScalarSl
   c.ctr.launches += 1;
 }
 template <class T>
-void k_scal_push(Context& c, long n, long ld, T* x, real_t<T> a, void** bases_dev, int rank, int world, unsigned long long epoch) {
-  scal_push_kernel<T><<<l1_grid<T>(c, n), kThreads, 0, c.stream>>>(n, ld, x, a, bases_dev, rank, world, c.ticket, epoch);
+void k_scal_push(Context& c, long n, long ld, T* x, real_t<T> a, void** bases_dev, int rank, int world, unsigned long long epoch,
+                 bool staggered, T* self_slice) {
+  if (staggered) {
+    scal_local_kernel<T><<<l1_grid<T>(c, n), kThreads, 0, c.stream>>>(n, x, a, self_slice);
+    PB_LAUNCH_CHECK();
+    PB_CUDA(cudaEventRecord(c.ev_fork, c.stream));
+    PB_CUDA(cudaStreamWaitEvent(c.stream2, c.ev_fork, 0));
+    scal_push_kernel<T, true><<<l1_grid<T>(c, n), kThreads, 0, c.stream2>>>(n, ld, x, a, bases_dev, rank, world, c.tickets8, epoch);
+    c.ctr.launches += 1;
+  } else
+    scal_push_kernel<T, false><<<l1_grid<T>(c, n), kThreads, 0, c.stream>>>(n, ld, x, a, bases_dev, rank, world, c.tickets8, epoch);
   PB_LAUNCH_CHECK();
   c.ctr.launches += 1;
 }
-void k_wait_flags(Context& c, const unsigned long long* flags, int world, unsigned long long epoch) {
-  wait_flags_kernel<<<1, 32, 0, c.stream>>>(flags, world, epoch, c.host_err_dev);
+void k_wait_flags(Context& c, const unsigned long long* flags, unsigned int src_mask, unsigned long long epoch) {
+  if (src_mask == 0u) return;
+  wait_flags_kernel<<<1, 32, 0, c.stream>>>(flags, src_mask, epoch, c.host_err_dev);
   PB_LAUNCH_CHECK();
   c.ctr.launches += 1;
 }
@@ -253,7 +303,7 @@ template <class T> void k_larnv_nrm(Context& c, long n, T* x, const int iseed[4]
   template void k_scal<T>(Context&, long, T*, real_t<T>);                         \
   template void k_scal_inv_slot<T>(Context&, long, T*, const ScalarSlot*);        \
   template void k_zero<T>(Context&, long, T*);                                    \
-  template void k_scal_push<T>(Context&, long, long, T*, real_t<T>, void**, int, int, unsigned long long); \
+  template void k_scal_push<T>(Context&, long, long, T*, real_t<T>, void**, int, int, unsigned long long, bool, T*); \
   template void k_axpy_nrm<T>(Context&, long, T, const T*, T*, Pending*);         \
   template void k_dotc<T>(Context&, long, const T*, const T*, Pending*);          \
   template void k_nrm2<T>(Context&, long, const T*, Pending*);                    \
