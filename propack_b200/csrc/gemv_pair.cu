@@ -53,14 +53,14 @@ template <class T> __device__ inline T fold4(T a0, T a1, T a2, T a3, int lane) {
 
 template <class T>
 __global__ void __launch_bounds__(kThreads, 2)
-gemv_t_kernel(long L, int l, const T* __restrict__ V, long ldv, const T* __restrict__ q, T* __restrict__ part, int lpad) {
+gemv_t_kernel(long L, int l, const T* __restrict__ V, long ldv, const T* __restrict__ q, T* __restrict__ part, int lpad, int chunk) {
   constexpr int VEC = Pack<T>::N;
   constexpr int WROWS = 32 * VEC * GT_S;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   T* hs = reinterpret_cast<T*>(smem_raw);  // [8][GT_CHUNK]
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  const int c_begin = blockIdx.y * GT_CHUNK;
-  const int c_end = min(l, c_begin + GT_CHUNK);
+  const int c_begin = blockIdx.y * chunk;   // chunk <= GT_CHUNK: the l columns are split EVENLY over gridDim.y slices
+  const int c_end = min(l, c_begin + chunk);
   const int nc = c_end - c_begin;
   for (int i = threadIdx.x; i < 8 * GT_CHUNK; i += kThreads) hs[i] = zero_<T>();
   __syncthreads();
@@ -290,7 +290,9 @@ template <class T> void k_gemv_t(Context& c, long L, int l, const T* V, long ldv
   if (l <= 0) return;
   constexpr int VEC = Pack<T>::N;
   const long wrows = 32L * VEC * GT_S;
+  // column slices of equal width (a 256 + 44 split of l = 300 would leave half the CTAs with 15% of the work)
   const int nchunks = ceil_div(l, GT_CHUNK);
+  const int chunk = ceil_div(ceil_div(l, nchunks), GT_CG) * GT_CG;
   int gx = (int)std::min<long>(ceil_div(L, wrows * 8), std::max(1, (2 * c.num_sms) / nchunks));
   if (gx < 1) gx = 1;
   const int lpad = (l + 3) / 4 * 4;
@@ -301,7 +303,7 @@ template <class T> void k_gemv_t(Context& c, long L, int l, const T* V, long ldv
     PB_CUDA(cudaFuncSetAttribute(gemv_t_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set = true;
   }
-  gemv_t_kernel<T><<<dim3(gx, nchunks), kThreads, smem, c.stream>>>(L, l, V, ldv, q, part, lpad);
+  gemv_t_kernel<T><<<dim3(gx, nchunks), kThreads, smem, c.stream>>>(L, l, V, ldv, q, part, lpad, chunk);
   PB_LAUNCH_CHECK();
   if (c.dist_reduce && c.coef_table != nullptr && l <= Comm::kCoefMax) {
     // fused: finalize + cross-rank all-reduce of the coefficients over NVLink peer memory, one launch
