@@ -84,6 +84,7 @@ class Context {
   // set-aside hurts the streamed operands more than it helps x -- so it is OFF by default (PROPACK_B200_L2_PERSIST=1 or
   // propack_b200_set_option("l2_persist", 1) to experiment).
   bool l2_persist = false;
+  bool l2_limit_set = false;
   size_t l2_persist_max = 0, l2_window_max = 0;
   const void* l2_win_ptr = nullptr; size_t l2_win_bytes = 0;
   void set_l2_window(const void* p, size_t bytes);
