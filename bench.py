@@ -216,6 +216,8 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    # torchrun exports OMP_NUM_THREADS=1 to every rank; the CPU arm uses all the host cores it can (set before libgomp loads)
+    os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
     A, u0, k, kmax, tol = make_matrix(args.workload)
     vals, secs, cores = [], [], 1
     note = ""
