@@ -42,6 +42,12 @@ static Csr make_random(int rows, int cols, double mean, uint64_t seed) {
   return A;
 }
 
+// cache-operator experiments: streamed operands / gathers that do not allocate L1 lines
+__device__ inline int ld_na_i32(const int* p) { int v; asm volatile("ld.global.nc.L1::no_allocate.b32 %0, [%1];" : "=r"(v) : "l"(p)); return v; }
+__device__ inline double ld_na_f64(const double* p) { double v; asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p)); return v; }
+__device__ inline double ld_gather_na(const double* p) { double v; asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p)); return v; }
+__device__ inline double ld_gather_el(const double* p) { double v; asm volatile("ld.global.nc.L1::evict_last.f64 %0, [%1];" : "=d"(v) : "l"(p)); return v; }
+
 __device__ inline double warp_sum(double v) { for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o); return v; }
 
 // ---------------------------------------------------------------------------------------------------
@@ -54,13 +60,19 @@ __global__ void __launch_bounds__(256) k_floor(long nnz, const int* __restrict__
   for (long p = (long)blockIdx.x * 1024 + threadIdx.x; p < nnz; p += stride) {
     int c[4]; double a[4];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) { long q = p + u * 256; c[u] = q < nnz ? __ldcs(ci + q) : 0; a[u] = q < nnz ? __ldcs(va + q) : 0.0; }
+    for (int u = 0; u < 4; ++u) {
+      long q = p + u * 256;
+      if (MODE >= 5) { c[u] = q < nnz ? ld_na_i32(ci + q) : 0; a[u] = q < nnz ? ld_na_f64(va + q) : 0.0; }
+      else { c[u] = q < nnz ? __ldcs(ci + q) : 0; a[u] = q < nnz ? __ldcs(va + q) : 0.0; }
+    }
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       double xv;
       if (MODE == 0) xv = (double)c[u];
       else if (MODE == 1) xv = __ldg(x + c[u]);
       else if (MODE == 2) xv = __ldcg(x + c[u]);
+      else if (MODE == 4) xv = ld_gather_na(x + c[u]);
+      else if (MODE == 6) xv = ld_gather_el(x + c[u]);
       else xv = x[c[u]];
       acc = fma(a[u], xv, acc);
     }
@@ -399,7 +411,7 @@ __global__ void __launch_bounds__(256) k_subwarp_ilp(Csr A, const double* __rest
 // independent gathers, products go to the warp's shared-memory slice; phase 2 reduces each row with LPR lanes.
 // The next group's row pointers are prefetched while the current group's gathers are in flight.
 // ---------------------------------------------------------------------------------------------------
-template <int WARPS, int MAXNNZ, int U>
+template <int WARPS, int MAXNNZ, int U, int NA = 0>
 __global__ void __launch_bounds__(WARPS * 32) k_warp_group_g(Csr A, int lpr_log2, const double* __restrict__ x, double* __restrict__ y, double coef,
                                                              const double* __restrict__ prev, double* nrm2) {
   __shared__ double prod[WARPS][MAXNNZ];
@@ -431,11 +443,11 @@ __global__ void __launch_bounds__(WARPS * 32) k_warp_group_g(Csr A, int lpr_log2
       for (int i0 = 0; i0 < nn; i0 += U * 32) {
         int c[U]; double a[U], xv[U];
 #pragma unroll
-        for (int u = 0; u < U; ++u) { const int i = i0 + u * 32 + lane; c[u] = i < nn ? __ldcs(cip + i) : -1; }
+        for (int u = 0; u < U; ++u) { const int i = i0 + u * 32 + lane; c[u] = i < nn ? (NA >= 1 ? ld_na_i32(cip + i) : __ldcs(cip + i)) : -1; }
 #pragma unroll
-        for (int u = 0; u < U; ++u) { const int i = i0 + u * 32 + lane; a[u] = i < nn ? __ldcs(vap + i) : 0.0; }
+        for (int u = 0; u < U; ++u) { const int i = i0 + u * 32 + lane; a[u] = i < nn ? (NA >= 1 ? ld_na_f64(vap + i) : __ldcs(vap + i)) : 0.0; }
 #pragma unroll
-        for (int u = 0; u < U; ++u) xv[u] = c[u] >= 0 ? __ldg(x + c[u]) : 0.0;
+        for (int u = 0; u < U; ++u) xv[u] = c[u] >= 0 ? (NA == 2 ? ld_gather_na(x + c[u]) : NA == 3 ? ld_gather_el(x + c[u]) : __ldg(x + c[u])) : 0.0;
 #pragma unroll
         for (int u = 0; u < U; ++u) { const int i = i0 + u * 32 + lane; if (i < nn) pw[i] = a[u] * xv[u]; }
       }
@@ -508,91 +520,24 @@ int main(int argc, char** argv) {
   const int g4 = sms * 8;
   run("floor stream-only", [&](Csr& M, double* xi, double* yo) { k_floor<0><<<g4, 256>>>(M.nnz, M.ci, M.va, xi, out); }, false);
   run("floor gather ld.nc", [&](Csr& M, double* xi, double* yo) { k_floor<1><<<g4, 256>>>(M.nnz, M.ci, M.va, xi, out); }, false);
-  run("floor gather ld.cg", [&](Csr& M, double* xi, double* yo) { k_floor<2><<<g4, 256>>>(M.nnz, M.ci, M.va, xi, out); }, false);
-  run("floor gather ld", [&](Csr& M, double* xi, double* yo) { k_floor<3><<<g4, 256>>>(M.nnz, M.ci, M.va, xi, out); }, false);
-  for (int mult : {2, 4, 16}) {
-    char nm[64]; snprintf(nm, 64, "floor gather ld.nc grid=%dxSM", mult);
-    run(nm, [&](Csr& M, double* xi, double* yo) { k_floor<1><<<sms * mult, 256>>>(M.nnz, M.ci, M.va, xi, out); }, false);
-  }
-  run("K3 thread/row", [&](Csr& M, double* xi, double* yo) { k_thread_row<<<(M.rows + 255) / 256, 256>>>(M, xi, yo, -0.5, prev, nrm); }, true);
-  run("K2 subwarp LPR=2", [&](Csr& M, double* xi, double* yo) { k_subwarp<2><<<(M.rows + 127) / 128, 256>>>(M, xi, yo, -0.5, prev, nrm); }, true);
-  run("K2 subwarp LPR=4", [&](Csr& M, double* xi, double* yo) { k_subwarp<4><<<(M.rows + 63) / 64, 256>>>(M, xi, yo, -0.5, prev, nrm); }, true);
-  run("K2 subwarp LPR=8", [&](Csr& M, double* xi, double* yo) { k_subwarp<8><<<(M.rows + 31) / 32, 256>>>(M, xi, yo, -0.5, prev, nrm); }, true);
-  run("K2 subwarp LPR=4 persistent", [&](Csr& M, double* xi, double* yo) { k_subwarp<4><<<sms * 8, 256>>>(M, xi, yo, -0.5, prev, nrm); }, true);
-  run("K4 warp-group W8 N512 U4", [&](Csr& M, double* xi, double* yo) { k_warp_group<8, 512, 4><<<sms * 6, 256>>>(M, xi, yo, -0.5, prev, nrm); }, true);
-  run("K4 warp-group W8 N512 U8", [&](Csr& M, double* xi, double* yo) { k_warp_group<8, 512, 8><<<sms * 6, 256>>>(M, xi, yo, -0.5, prev, nrm); }, true);
-  run("K4 warp-group W8 N512 U4 nonpers", [&](Csr& M, double* xi, double* yo) { k_warp_group<8, 512, 4><<<(M.rows + 255) / 256, 256>>>(M, xi, yo, -0.5, prev, nrm); }, true);
-  run("K4 warp-group W4 N512 U4 x12", [&](Csr& M, double* xi, double* yo) { k_warp_group<4, 512, 4><<<sms * 12, 128>>>(M, xi, yo, -0.5, prev, nrm); }, true);
-  run("K4 warp-group W16 N384 U2", [&](Csr& M, double* xi, double* yo) { k_warp_group<16, 384, 2><<<sms * 3, 512>>>(M, xi, yo, -0.5, prev, nrm); }, true);
-  run("K5 warp-group TMA-bulk W8", [&](Csr& M, double* xi, double* yo) { k_warp_group_tma<8, 352><<<sms * 4, 256>>>(M, xi, yo, -0.5, prev, nrm); }, true);
-  run("K5 warp-group TMA-bulk W4 x6", [&](Csr& M, double* xi, double* yo) { k_warp_group_tma<4, 512><<<sms * 6, 128>>>(M, xi, yo, -0.5, prev, nrm); }, true);
-  run("K6 cta-panel NB4096 LPR4", [&](Csr& M, double* xi, double* yo) { k_cta_panel<4096, 4><<<sms * 6, 256>>>(M, xi, yo, -0.5, prev, nrm); }, true);
-  run("K6 cta-panel nonpersistent", [&](Csr& M, double* xi, double* yo) { k_cta_panel<4096, 4><<<(M.rows + 255) / 256, 256>>>(M, xi, yo, -0.5, prev, nrm); }, true);
-
-  // panel descriptors for K8 (rows <= RMAX, nnz <= NB; a longer row would stand alone -- none at these densities)
-  auto make_panels = [&](const Csr& M, int NB, int RMAX, PanelDesc** dout) {
-    std::vector<int> rp(M.rows + 1);
-    CK(cudaMemcpy(rp.data(), M.rp, 4L * (M.rows + 1), cudaMemcpyDeviceToHost));
-    std::vector<PanelDesc> d;
-    int r = 0;
-    while (r < M.rows) {
-      d.push_back({r, rp[r]});
-      int e = r; 
-      while (e < M.rows && e - r < RMAX && rp[e + 1] - rp[r] <= NB) ++e;
-      if (e == r) { printf("row longer than NB\n"); exit(1); }
-      r = e;
-    }
-    d.push_back({M.rows, rp[M.rows]});
-    CK(cudaMalloc(dout, sizeof(PanelDesc) * d.size()));
-    CK(cudaMemcpy(*dout, d.data(), sizeof(PanelDesc) * d.size(), cudaMemcpyHostToDevice));
-    return (int)d.size() - 1;
-  };
-#define RUN_K8(THREADS, NB, RMAX, STAGES, U, CPS, CARVE)                                                               \
-  {                                                                                                                    \
-    PanelDesc *dA, *dB;                                                                                                \
-    const int nA = make_panels(A, NB, RMAX, &dA), nB = make_panels(B, NB, RMAX, &dB);                                  \
-    const size_t smem = sizeof(PanelStage<NB, RMAX>) * STAGES;                                                         \
-    CK(cudaFuncSetAttribute(k_tma_panel<THREADS, NB, RMAX, STAGES, U>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    CK(cudaFuncSetAttribute(k_tma_panel<THREADS, NB, RMAX, STAGES, U>, cudaFuncAttributePreferredSharedMemoryCarveout, CARVE)); \
-    char nm[96]; snprintf(nm, 96, "K8 T%d NB%d R%d S%d U%d x%d smem/SM=%dKB carve=%d", THREADS, NB, RMAX, STAGES, U, CPS, (int)(smem * CPS / 1024), CARVE); \
-    run(nm, [&](Csr& M, double* xi, double* yo) {                                                                     \
-      const bool isA = (&M == &A);                                                                                     \
-      k_tma_panel<THREADS, NB, RMAX, STAGES, U><<<sms * CPS, THREADS, smem>>>(M, isA ? dA : dB, isA ? nA : nB, xi, yo, -0.5, prev, nrm); \
-    }, true);                                                                                                          \
-    cudaFree(dA); cudaFree(dB);                                                                                        \
-  }
-  RUN_K8(256, 1024, 128, 2, 4, 4, 50)
+  run("floor gather ld.nc.L1::no_allocate", [&](Csr& M, double* xi, double* yo) { k_floor<4><<<g4, 256>>>(M.nnz, M.ci, M.va, xi, out); }, false);
+  run("floor streams no_allocate + gather ld", [&](Csr& M, double* xi, double* yo) { k_floor<5><<<g4, 256>>>(M.nnz, M.ci, M.va, xi, out); }, false);
+  run("floor streams no_allocate + gather evict_last", [&](Csr& M, double* xi, double* yo) { k_floor<6><<<g4, 256>>>(M.nnz, M.ci, M.va, xi, out); }, false);
   int lprl = 0; { double mn = (double)A.nnz / A.rows; int rpg = 32; while (rpg > 1 && rpg * 1.3 * mn > 512) rpg >>= 1; while ((32 >> lprl) > rpg) ++lprl; }
-  printf("mean nnz/row %.1f -> lanes per row %d\n", (double)A.nnz / A.rows, 1 << lprl);
-#define RUN_K4(W, N, U, CPS, CARVE)                                                                                    \
+#define RUN_K4G(W, N, U, NA, CPS, CARVE)                                                                               \
   {                                                                                                                    \
-    CK(cudaFuncSetAttribute(k_warp_group<W, N, U>, cudaFuncAttributePreferredSharedMemoryCarveout, CARVE));            \
-    char nm[96]; snprintf(nm, 96, "K4 W%d N%d U%d x%d smem/SM=%dKB carve=%d", W, N, U, CPS, W * N * 8 * CPS / 1024, CARVE); \
-    run(nm, [&](Csr& M, double* xi, double* yo) { k_warp_group<W, N, U><<<sms * CPS, W * 32>>>(M, xi, yo, -0.5, prev, nrm); }, true); \
+    CK(cudaFuncSetAttribute(k_warp_group_g<W, N, U, NA>, cudaFuncAttributePreferredSharedMemoryCarveout, CARVE));      \
+    char nm[96]; snprintf(nm, 96, "K4g W%d N%d U%d NA%d x%d carve=%d", W, N, U, NA, CPS, CARVE);                       \
+    run(nm, [&](Csr& M, double* xi, double* yo) { k_warp_group_g<W, N, U, NA><<<sms * CPS, W * 32>>>(M, lprl, xi, yo, -0.5, prev, nrm); }, true); \
   }
-#define RUN_K4G(W, N, U, CPS, CARVE)                                                                                   \
-  {                                                                                                                    \
-    CK(cudaFuncSetAttribute(k_warp_group_g<W, N, U>, cudaFuncAttributePreferredSharedMemoryCarveout, CARVE));          \
-    char nm[96]; snprintf(nm, 96, "K4g W%d N%d U%d x%d smem/SM=%dKB carve=%d", W, N, U, CPS, W * N * 8 * CPS / 1024, CARVE); \
-    run(nm, [&](Csr& M, double* xi, double* yo) { k_warp_group_g<W, N, U><<<sms * CPS, W * 32>>>(M, lprl, xi, yo, -0.5, prev, nrm); }, true); \
-  }
-  RUN_K4(8, 512, 4, 2, 30)
-  RUN_K4(8, 512, 4, 3, 45)
-  RUN_K4(8, 512, 4, 3, 35)
-  RUN_K4(8, 512, 4, 4, 60)
-  RUN_K4(8, 512, 8, 3, 45)
-  RUN_K4(4, 512, 4, 6, 45)
-  RUN_K4(4, 512, 4, 8, 60)
-  RUN_K4G(8, 512, 4, 3, 45)
-  RUN_K4G(8, 512, 8, 3, 45)
-  RUN_K4G(8, 512, 12, 3, 45)
-  RUN_K4G(8, 512, 4, 4, 60)
-  RUN_K4G(8, 512, 12, 4, 60)
-  RUN_K4G(4, 512, 12, 6, 45)
-  RUN_K4G(4, 512, 12, 8, 60)
-  RUN_K4G(16, 384, 12, 2, 45)
-  RUN_K4G(8, 384, 12, 4, 45)
-  RUN_K4G(8, 384, 12, 5, 55)
+  RUN_K4G(8, 512, 4, 0, 3, 45)
+  RUN_K4G(8, 512, 4, 1, 3, 45)
+  RUN_K4G(8, 512, 4, 2, 3, 45)
+  RUN_K4G(8, 512, 4, 3, 3, 45)
+  RUN_K4G(8, 512, 4, 1, 4, 60)
+  RUN_K4G(8, 512, 8, 1, 3, 45)
+  RUN_K4G(8, 512, 6, 0, 3, 45)
+  RUN_K4G(8, 512, 6, 1, 3, 45)
   return 0;
 
 }
