@@ -188,3 +188,17 @@ def test_refinebounds_matches_oracle(oracle):
         L.drefinebounds_(C.byref(C.c_int(n)), C.byref(C.c_int(k)), _cd(theta), _cd(b1), C.byref(C.c_double(1e-13)), C.byref(C.c_double(1e-12)))
         O.oracle_refinebounds_d(C.c_int(n), C.c_int(k), _cd(theta), _cd(b2), C.c_double(1e-13), C.c_double(1e-12))
         assert np.allclose(b1, b2, rtol=1e-12, atol=0)
+
+
+def test_fortran_interface_module_names_exist_in_the_library():
+    """include/propack_b200.f90 (never compiled here) must at least bind to symbols the library really exports."""
+    import re
+    from propack_b200 import _lib
+    L = _lib.lib()
+    src = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include", "propack_b200.f90")).read()
+    names = re.findall(r"bind\(C, name='([A-Za-z0-9_]+)'\)", src)
+    assert len(names) >= 8
+    for n in names:
+        assert hasattr(L, n), n
+    for p in "sdcz":
+        assert hasattr(L, f"propack_b200_aprod_{p}_")
