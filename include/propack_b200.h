@@ -252,6 +252,10 @@ int propack_b200_csr_create_sharded_z(int m_global, int n_global, const int* row
 /* local slice sizes of a solver session (U is m_local x ucols with leading dimension ldu on the device, ...) */
 int propack_b200_solver_local_rows(int solver, int* m_local, int* n_local, long* ldu, long* ldv);
 
+/* host-only test hook: leading Ritz values and |last component of the left singular vector| of the (j+1) x j lower
+ * bidiagonal (alpha, beta) by the reference route (method 0: dbdqr + dbdsqr, double/dlansvd.F:193-199) or the fast route
+ * used for large j (method 1: dqds + inverse iteration); returns 1 when method 1 declines */
+int propack_b200_host_ritz_bounds_d(int j, const double* alpha, const double* beta, int K, int method, double* theta, double* last);
 int propack_b200_init(void);                         /* create the context on the current device; 0 or negative */
 int propack_b200_set_stream(void* cuda_stream);      /* run on a caller stream (e.g. torch's current stream) */
 int propack_b200_set_lapack(const char* path);       /* shared object providing {d,s}bdsqr / {d,s}bdsdc */

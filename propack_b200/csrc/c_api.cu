@@ -824,6 +824,21 @@ int propack_b200_solver_local_rows(int solver, int* m_local, int* n_local, long*
   PB_API_CATCH(return code__)
 }
 
+// Host-only test hook (no device needed): leading Ritz values / last-row components of the (j+1) x j lower bidiagonal by
+// method 0 = the reference route (dbdqr + dbdsqr, dlansvd.F:193-199) or 1 = host::ritz_leading.  Returns 0, or 1 when
+// method 1 declined (the driver then falls back to method 0).
+int propack_b200_host_ritz_bounds_d(int j, const double* alpha, const double* beta, int K, int method, double* theta, double* last) {
+  PB_API_TRY
+  if (method == 1) return host::ritz_leading(j, alpha, beta, K, theta, last) ? 0 : 1;
+  std::vector<double> th(alpha, alpha + j), ee(beta, beta + j), wb((size_t)j + 2, 0.0);
+  int info = 0;
+  host::bidiag_qr<double>(false, false, j, th.data(), ee.data(), wb[j - 1], wb[j], nullptr, 0);
+  host::bdsqr_row(j, th.data(), ee.data(), wb.data(), &info);
+  for (int i = 0; i < K; ++i) { theta[i] = th[i]; last[i] = std::fabs(wb[i]); }
+  return info == 0 ? 0 : -1;
+  PB_API_CATCH(return code__)
+}
+
 // ---- runtime --------------------------------------------------------------------------------------------------
 int propack_b200_init(void) {
   PB_API_TRY

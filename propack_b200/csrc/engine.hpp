@@ -7,6 +7,7 @@
 // problem.  There is no CPU fallback: every vector operation below is a CUDA kernel launch.
 #pragma once
 #include <cmath>
+#include <cstdlib>
 #include <functional>
 #include <memory>
 #include <stdexcept>
@@ -24,6 +25,12 @@ namespace pb {
 template <class T>
 using aprod_f77_t = void (*)(const char* transa, const int* m, const int* n, const T* x, T* y, void* parm, int* iparm,
                              size_t transa_len);
+
+// PROPACK_B200_FAST_RITZ_BOUNDS=0 forces the reference's xBDSQR route for the per-iteration Ritz bounds (cross-check)
+inline bool fast_ritz_bounds() {
+  static const bool on = [] { const char* e = std::getenv("PROPACK_B200_FAST_RITZ_BOUNDS"); return !(e && e[0] == '0'); }();
+  return on;
+}
 
 inline void set_scalar(float& s, double re, double) { s = (float)re; }
 inline void set_scalar(double& s, double re, double) { s = re; }

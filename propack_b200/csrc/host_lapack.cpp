@@ -3,6 +3,8 @@
 #include <dlfcn.h>
 #include <glob.h>
 
+#include <algorithm>
+#include <cmath>
 #include <cstdlib>
 #include <stdexcept>
 #include <string>
@@ -21,7 +23,12 @@ typedef void (*dbdsdc_t)(const char*, const char*, const int*, double*, double*,
                          const int*, double*, int*, double*, int*, int*, size_t, size_t);
 typedef void (*sbdsdc_t)(const char*, const char*, const int*, float*, float*, float*, const int*, float*,
                          const int*, float*, int*, float*, int*, int*, size_t, size_t);
+typedef void (*dlasq1_t)(const int*, double*, double*, double*, int*);
+typedef void (*dstein_t)(const int*, const double*, const double*, const int*, const double*, const int*, const int*, double*,
+                         const int*, double*, int*, int*, int*);
 }
+dlasq1_t p_dlasq1 = nullptr;   // optional (ritz_leading)
+dstein_t p_dstein = nullptr;
 dbdsqr_t p_dbdsqr = nullptr;
 sbdsqr_t p_sbdsqr = nullptr;
 dbdsdc_t p_dbdsdc = nullptr;
@@ -43,6 +50,8 @@ bool try_bind(const std::string& path) {
   sbdsdc_t d = (sbdsdc_t)sym("sbdsdc");
   if (!(a && b && c && d)) { dlclose(h); return false; }
   p_dbdsqr = a; p_sbdsqr = b; p_dbdsdc = c; p_sbdsdc = d;
+  p_dlasq1 = (dlasq1_t)sym("dlasq1");
+  p_dstein = (dstein_t)sym("dstein");
   return true;
 }
 }  // namespace
@@ -99,6 +108,47 @@ void bdsdc_full(int n, float* d, float* e, float* U, int ldu, float* VT, int ldv
   float q[1]; int iq[1];
   p_sbdsdc("U", "I", &n, d, e, U, &ldu, VT, &ldvt, q, iq, work.data(), iwork.data(), info, 1, 1);
 }
+
+bool ritz_leading(int j, const double* alpha, const double* beta, int K, double* theta, double* last) {
+  bind_lapack();
+  if (!p_dlasq1 || !p_dstein || j < 2 || K < 1 || K > j) return false;
+  double amax = 0;
+  for (int i = 0; i < j; ++i) amax = std::max(amax, std::max(std::fabs(alpha[i]), std::fabs(beta[i])));
+  for (int i = 0; i < j; ++i)
+    if (!(std::fabs(alpha[i]) > 1e-13 * amax) || !(std::fabs(beta[i]) > 1e-13 * amax)) return false;  // (nearly) reducible
+  // 1. singular values: QR-reduce the (j+1) x j lower bidiagonal to j x j upper (dbdqr's rotations, dbsvd.F:128-147), dqds
+  std::vector<double> d(alpha, alpha + j), e(beta, beta + j), work(4 * (size_t)j + 8);
+  for (int i = 0; i < j - 1; ++i) {
+    const double r = std::hypot(d[i], e[i]), cs = d[i] / r, sn = e[i] / r;
+    d[i] = r; e[i] = sn * d[i + 1]; d[i + 1] = cs * d[i + 1];
+  }
+  d[j - 1] = std::hypot(d[j - 1], e[j - 1]); e[j - 1] = 0;
+  int info = 0;
+  p_dlasq1(&j, d.data(), e.data(), work.data(), &info);
+  if (info != 0) return false;
+  for (int i = 0; i + 1 < K; ++i)
+    if (!(d[i] > d[i + 1])) return false;               // repeated leading values: leave it to the reference route
+  // 2. eigenvectors of the Golub-Kahan tridiagonal (order u_1 v_1 u_2 v_2 ... u_j v_j u_{j+1}; zero diagonal,
+  //    off-diagonals alpha_1 beta_1 alpha_2 beta_2 ... alpha_j beta_j) for the eigenvalues +sigma_K <= ... <= +sigma_1
+  const int N = 2 * j + 1;
+  std::vector<double> dz((size_t)N, 0.0), off((size_t)N), w((size_t)K), Z((size_t)N * K), wk(5 * (size_t)N);
+  std::vector<int> iblock((size_t)N, 1), isplit((size_t)N, 0), iwk((size_t)N), ifail((size_t)K, 0);
+  for (int i = 0; i < j; ++i) { off[2 * i] = alpha[i]; off[2 * i + 1] = beta[i]; }
+  for (int i = 0; i < K; ++i) w[i] = d[K - 1 - i];
+  isplit[0] = N;
+  p_dstein(&N, dz.data(), off.data(), &K, w.data(), iblock.data(), isplit.data(), Z.data(), &N, wk.data(), iwk.data(), ifail.data(), &info);
+  if (info != 0) return false;
+  for (int i = 0; i < K; ++i) {
+    const double* z = Z.data() + (size_t)(K - 1 - i) * N;   // column of sigma_i (descending order out)
+    double un = 0;
+    for (int t = 0; t < N; t += 2) un += z[t] * z[t];
+    if (!(un > 0.25 && un < 0.75)) return false;             // the u-part of a unit eigenvector has norm^2 1/2
+    theta[i] = d[i];
+    last[i] = std::fabs(z[N - 1]) / std::sqrt(un);
+  }
+  return true;
+}
+bool ritz_leading(int, const float*, const float*, int, float*, float*) { return false; }
 
 }  // namespace host
 }  // namespace pb

@@ -20,5 +20,16 @@ void bdsqr_row(int n, float* d, float* e, float* urow, int* info);
 void bdsdc_full(int n, double* d, double* e, double* U, int ldu, double* VT, int ldvt, int* info);
 void bdsdc_full(int n, float* d, float* e, float* U, int ldu, float* VT, int ldvt, int* info);
 
+// Leading K Ritz values of the (j+1) x j lower bidiagonal B (diag alpha, sub-diag beta) and the last components of
+// their left singular vectors -- the quantities the non-restarted driver needs per outer iteration (error bounds
+// bnd(i) = |rnorm * u_i(j+1)|, dlansvd.F:196-209) -- without the O(j^2) QR sweep over all j values: singular values by
+// dqds (xLASQ1, high relative accuracy) on the QR-reduced bidiagonal, vectors by inverse iteration (xSTEIN, with its
+// reorthogonalisation inside clusters) on the Golub-Kahan tridiagonal of B, whose eigenvector for +sigma_i interleaves
+// (u_i, v_i).  theta[0:K] descending, last[0:K] = |u_i(j+1)| for unit u_i.  Returns false (nothing written) when the
+// routines are not available, B has a zero / negligible entry (reducible problem) or xSTEIN reports a failure: the
+// caller then takes the reference's xBDSQR route.  The float overload always returns false.
+bool ritz_leading(int j, const double* alpha, const double* beta, int K, double* theta, double* last);
+bool ritz_leading(int j, const float* alpha, const float* beta, int K, float* theta, float* last);
+
 }  // namespace host
 }  // namespace pb

@@ -1,0 +1,80 @@
+"""CPU: the fast route for the per-iteration Ritz values / error bounds of the non-restarted driver
+(host::ritz_leading: dqds + inverse iteration on the Golub-Kahan tridiagonal) against the reference route
+(dbdqr + dbdsqr, dlansvd.F:193-209) on real Lanczos bidiagonals produced by the oracle."""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+@pytest.fixture(scope="module")
+def lanczos_bidiagonal(oracle):
+    """alpha, beta of 420 steps of DLANBPRO (oracle) on a 20000 x 20000 random sparse matrix; also rnorm = beta_j."""
+    rng = np.random.default_rng(0)
+    m = n = 20000
+    A = sp.random_array((m, n), density=5e-4, format="csr", rng=rng, data_sampler=rng.standard_normal)
+    A.sort_indices()
+    steps = 420
+    L = oracle.lib()
+    op = oracle.Operator(A, np.float64)
+    U = np.zeros((m, steps + 1), order="F"); V = np.zeros((n, steps), order="F")
+    U[:, 0] = np.random.default_rng(1).uniform(size=m)
+    B = np.zeros((steps, 2), order="F")
+    eps = np.finfo(np.float64).eps
+    dopt = np.array([np.sqrt(eps), eps ** 0.75, 0.0]); iopt = np.array([1, 1], dtype=np.int32)
+    kk, rn, ierr = C.c_int(steps), C.c_double(float(np.linalg.norm(U[:, 0]))), C.c_int(0)
+    L.oracle_lanbpro_d(C.c_int(m), C.c_int(n), C.c_int(0), C.byref(kk), *op.args(), _p(U), C.c_long(m), _p(V), C.c_long(n), _p(B),
+                       C.c_int(steps), C.byref(rn), _p(dopt), _p(iopt), C.byref(ierr))
+    assert kk.value == steps
+    return B[:, 0].copy(), B[:, 1].copy()
+
+
+def _bounds(j, alpha, beta, K, method):
+    from propack_b200 import _lib
+    L = _lib.lib()
+    th, last = np.zeros(K), np.zeros(K)
+    rc = L.propack_b200_host_ritz_bounds_d(C.c_int(j), _p(np.ascontiguousarray(alpha[:j])), _p(np.ascontiguousarray(beta[:j])), C.c_int(K),
+                                           C.c_int(method), _p(th), _p(last))
+    return rc, th, last
+
+
+@pytest.mark.parametrize("j", [128, 151, 226, 326, 420])
+def test_fast_route_matches_reference_route(lanczos_bidiagonal, j):
+    alpha, beta = lanczos_bidiagonal
+    K = 54
+    rc0, th0, b0 = _bounds(j, alpha, beta, K, 0)
+    rc1, th1, b1 = _bounds(j, alpha, beta, K, 1)
+    assert rc0 == 0 and rc1 == 0
+    assert np.max(np.abs(th1 - th0) / th0) < 1e-13                       # Ritz values
+    # last components of the left singular vectors: both routes are normwise accurate (errors ~ eps / gap); what the
+    # driver compares them with is tol * theta / rnorm >= 16 eps, so agreement to 1e-12 absolute decides identically
+    assert np.max(np.abs(b1 - b0)) < 1e-12
+    big = b0 > 1e-9
+    assert np.max(np.abs(b1[big] - b0[big]) / b0[big]) < 1e-6
+    # same convergence decisions as the driver takes (dlansvd.F:207-236) for a range of tolerances
+    rnorm = beta[j - 1]
+    for tol in (1e-6, 1e-10, 1e-13):
+        conv = lambda th, b: int(np.argmin(np.append(np.abs(rnorm * b) <= tol * th, False)))
+        assert conv(th0, b0) == conv(th1, b1)
+
+
+def test_fast_route_declines_on_reducible_and_repeated_input():
+    from propack_b200 import _lib
+    j, K = 140, 20
+    rng = np.random.default_rng(0)
+    alpha, beta = rng.uniform(1, 2, j), rng.uniform(1, 2, j)
+    beta[70] = 0.0                                   # B splits: the Golub-Kahan matrix is reducible
+    assert _bounds(j, alpha, beta, K, 1)[0] == 1
+    alpha[:] = 1.0; beta[:] = 1e-16                  # negligible coupling
+    assert _bounds(j, alpha, beta, K, 1)[0] == 1
+    assert _bounds(j, alpha, beta, K, 0)[0] == 0     # the reference route always answers
