@@ -256,6 +256,9 @@ int propack_b200_solver_local_rows(int solver, int* m_local, int* n_local, long*
  * bidiagonal (alpha, beta) by the reference route (method 0: dbdqr + dbdsqr, double/dlansvd.F:193-199) or the fast route
  * used for large j (method 1: dqds + inverse iteration); returns 1 when method 1 declines */
 int propack_b200_host_ritz_bounds_d(int j, const double* alpha, const double* beta, int K, int method, double* theta, double* last);
+/* host-only test hook: the (dim+1) x k and dim x k matrices that dritzvec (double/dritzvec.F:116-193) multiplies the Lanczos
+ * bases with, by the reference route (method 0) or the fast route (method 1; returns 1 when it declines) */
+int propack_b200_host_ritz_vectors_d(int dim, const double* alpha, const double* beta, int k, int method, double* WU, double* WV);
 int propack_b200_init(void);                         /* create the context on the current device; 0 or negative */
 int propack_b200_set_stream(void* cuda_stream);      /* run on a caller stream (e.g. torch's current stream) */
 int propack_b200_set_lapack(const char* path);       /* shared object providing {d,s}bdsqr / {d,s}bdsdc */

@@ -839,6 +839,23 @@ int propack_b200_host_ritz_bounds_d(int j, const double* alpha, const double* be
   PB_API_CATCH(return code__)
 }
 
+// Host-only test hook: the small matrices of dritzvec, WU ((dim+1) x k) and WV (dim x k), by the reference route
+// (method 0: dbdqr + dbdsdc) or the fast route (method 1: host::ritz_vectors_leading).  Returns 1 when method 1 declines.
+int propack_b200_host_ritz_vectors_d(int dim, const double* alpha, const double* beta, int k, int method, double* WU, double* WV) {
+  PB_API_TRY
+  std::vector<double> wu, wv;
+  if (method == 1) {
+    if (!host::ritz_vectors_leading(dim, alpha, beta, k, wu, wv)) return 1;
+  } else {
+    std::vector<double> D(alpha, alpha + dim), E(beta, beta + dim);
+    ritz_w_reference<double>(false, false, true, true, k, dim, D.data(), E.data(), wu, wv);
+  }
+  std::copy(wu.begin(), wu.end(), WU);
+  std::copy(wv.begin(), wv.end(), WV);
+  return 0;
+  PB_API_CATCH(return code__)
+}
+
 // ---- runtime --------------------------------------------------------------------------------------------------
 int propack_b200_init(void) {
   PB_API_TRY

@@ -214,36 +214,50 @@ template <class T> int Engine<T>::lanbpro(int k0, int& k, R* a, R* b, R& rnorm, 
 // ================================================================================================
 // dritzvec: host bidiagonal SVD (dbdqr + dbdsdc), then the two tall in-place GEMMs on device.
 // ================================================================================================
-template <class T> void Engine<T>::ritzvec(bool smallest, bool jobu, bool jobv, int k, int dim, R* D, R* E) {
-  Context::PhaseScope ps(c, PH_RITZ);
-  DistScope ds(c, dist);
+// The reference's route to the two small matrices of dritzvec (dritzvec.F:116-193): WU ((dim+1) x k, ld dim+1) and
+// WV (dim x k, ld dim) such that U(:,1:k) <- U(:,1:dim+1) WU and V(:,1:k) <- V(:,1:dim) WV.  D, E are overwritten.
+template <class R>
+void ritz_w_reference(bool ignorelast, bool smallest, bool want_u, bool want_v, int k, int dim, R* D, R* E, std::vector<R>& WU,
+                      std::vector<R>& WV) {
   std::vector<R> Mt((size_t)(dim + 1) * (dim + 1), R(0)), Qt((size_t)dim * dim, R(0)), P((size_t)dim * dim, R(0));
   R c1 = 0, c2 = 0;
   int info = 0;
-  host::bidiag_qr(dim == std::min(mg, ng), jobu, dim, D, E, c1, c2, Mt.data(), dim + 1);  // dritzvec.F:116
-  host::bdsdc_full(dim, D, E, P.data(), dim, Qt.data(), dim, &info);                    // :123
+  host::bidiag_qr(ignorelast, want_u, dim, D, E, c1, c2, Mt.data(), dim + 1);  // dritzvec.F:116
+  host::bdsdc_full(dim, D, E, P.data(), dim, Qt.data(), dim, &info);         // :123
   const int mstart = smallest ? dim - k : 0;  // 0-based first wanted row of X / Q^T
-  if (jobu) {
+  if (want_u) {
     // X = P^T M^T(1:dim,:) (:130), and the wanted product is U(:,1:dim+1) * X(mstart:mstart+k,:)^T (:160):
     // W (K=dim+1 x N=k) with W(l,jn) = X(mstart+jn, l)
-    std::vector<R> W((size_t)(dim + 1) * k);
+    WU.assign((size_t)(dim + 1) * k, R(0));
     for (int jn = 0; jn < k; ++jn)
       for (int l = 0; l < dim + 1; ++l) {
         R s = 0;
         const R* pc = P.data() + (size_t)(mstart + jn) * dim;  // column mstart+jn of P
         const R* mc = Mt.data() + (size_t)l * (dim + 1);       // column l of M^T (first dim rows)
         for (int t = 0; t < dim; ++t) s += pc[t] * mc[t];
-        W[(size_t)jn * (dim + 1) + l] = s;
+        WU[(size_t)jn * (dim + 1) + l] = s;
       }
-    k_gemm_tall<T>(c, m, k, dim + 1, U, ldu, W.data());
   }
-  if (jobv) {
+  if (want_v) {
     // V(:,1:k) = V(:,1:dim) * Qt(mstart:mstart+k,:)^T (:193): W(l,jn) = Qt(mstart+jn, l)
-    std::vector<R> W((size_t)dim * k);
+    WV.assign((size_t)dim * k, R(0));
     for (int jn = 0; jn < k; ++jn)
-      for (int l = 0; l < dim; ++l) W[(size_t)jn * dim + l] = Qt[(size_t)l * dim + mstart + jn];
-    k_gemm_tall<T>(c, n, k, dim, V, ldv, W.data());
+      for (int l = 0; l < dim; ++l) WV[(size_t)jn * dim + l] = Qt[(size_t)l * dim + mstart + jn];
   }
+}
+
+template <class T> void Engine<T>::ritzvec(bool smallest, bool jobu, bool jobv, int k, int dim, R* D, R* E) {
+  Context::PhaseScope ps(c, PH_RITZ);
+  DistScope ds(c, dist);
+  std::vector<R> WU, WV;
+  // Large Krylov dimension, largest triplets: the k leading singular vector pairs of B directly (dqds + inverse iteration
+  // on the Golub-Kahan tridiagonal) instead of a divide & conquer SVD of all dim pairs; the reference route is the fallback.
+  bool fast = false;
+  if (fast_ritz_bounds() && !smallest && dim >= 128 && dim != std::min(mg, ng) && k < dim)
+    fast = host::ritz_vectors_leading(dim, D, E, k, WU, WV);
+  if (!fast) ritz_w_reference<R>(dim == std::min(mg, ng), smallest, jobu, jobv, k, dim, D, E, WU, WV);
+  if (jobu) k_gemm_tall<T>(c, m, k, dim + 1, U, ldu, WU.data());
+  if (jobv) k_gemm_tall<T>(c, n, k, dim, V, ldv, WV.data());
   c.sync();
 }
 

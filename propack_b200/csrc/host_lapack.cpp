@@ -109,7 +109,9 @@ void bdsdc_full(int n, float* d, float* e, float* U, int ldu, float* VT, int ldv
   p_sbdsdc("U", "I", &n, d, e, U, &ldu, VT, &ldvt, q, iq, work.data(), iwork.data(), info, 1, 1);
 }
 
-bool ritz_leading(int j, const double* alpha, const double* beta, int K, double* theta, double* last) {
+namespace {
+// sigma (all j, descending) by dqds and the Golub-Kahan eigenvectors Z (N x K, column c <-> sigma_{K-1-c}) of the K leading ones
+bool leading_triplets(int j, const double* alpha, const double* beta, int K, std::vector<double>& sig, std::vector<double>& Z) {
   bind_lapack();
   if (!p_dlasq1 || !p_dstein || j < 2 || K < 1 || K > j) return false;
   double amax = 0;
@@ -117,7 +119,9 @@ bool ritz_leading(int j, const double* alpha, const double* beta, int K, double*
   for (int i = 0; i < j; ++i)
     if (!(std::fabs(alpha[i]) > 1e-13 * amax) || !(std::fabs(beta[i]) > 1e-13 * amax)) return false;  // (nearly) reducible
   // 1. singular values: QR-reduce the (j+1) x j lower bidiagonal to j x j upper (dbdqr's rotations, dbsvd.F:128-147), dqds
-  std::vector<double> d(alpha, alpha + j), e(beta, beta + j), work(4 * (size_t)j + 8);
+  std::vector<double> e(beta, beta + j), work(4 * (size_t)j + 8);
+  sig.assign(alpha, alpha + j);
+  std::vector<double>& d = sig;
   for (int i = 0; i < j - 1; ++i) {
     const double r = std::hypot(d[i], e[i]), cs = d[i] / r, sn = e[i] / r;
     d[i] = r; e[i] = sn * d[i + 1]; d[i + 1] = cs * d[i + 1];
@@ -131,23 +135,50 @@ bool ritz_leading(int j, const double* alpha, const double* beta, int K, double*
   // 2. eigenvectors of the Golub-Kahan tridiagonal (order u_1 v_1 u_2 v_2 ... u_j v_j u_{j+1}; zero diagonal,
   //    off-diagonals alpha_1 beta_1 alpha_2 beta_2 ... alpha_j beta_j) for the eigenvalues +sigma_K <= ... <= +sigma_1
   const int N = 2 * j + 1;
-  std::vector<double> dz((size_t)N, 0.0), off((size_t)N), w((size_t)K), Z((size_t)N * K), wk(5 * (size_t)N);
+  std::vector<double> dz((size_t)N, 0.0), off((size_t)N), w((size_t)K), wk(5 * (size_t)N);
   std::vector<int> iblock((size_t)N, 1), isplit((size_t)N, 0), iwk((size_t)N), ifail((size_t)K, 0);
+  Z.assign((size_t)N * K, 0.0);
   for (int i = 0; i < j; ++i) { off[2 * i] = alpha[i]; off[2 * i + 1] = beta[i]; }
   for (int i = 0; i < K; ++i) w[i] = d[K - 1 - i];
   isplit[0] = N;
   p_dstein(&N, dz.data(), off.data(), &K, w.data(), iblock.data(), isplit.data(), Z.data(), &N, wk.data(), iwk.data(), ifail.data(), &info);
-  if (info != 0) return false;
+  return info == 0;
+}
+}  // namespace
+
+bool ritz_leading(int j, const double* alpha, const double* beta, int K, double* theta, double* last) {
+  std::vector<double> sig, Z;
+  if (!leading_triplets(j, alpha, beta, K, sig, Z)) return false;
+  const int N = 2 * j + 1;
   for (int i = 0; i < K; ++i) {
     const double* z = Z.data() + (size_t)(K - 1 - i) * N;   // column of sigma_i (descending order out)
     double un = 0;
     for (int t = 0; t < N; t += 2) un += z[t] * z[t];
     if (!(un > 0.25 && un < 0.75)) return false;             // the u-part of a unit eigenvector has norm^2 1/2
-    theta[i] = d[i];
+    theta[i] = sig[i];
     last[i] = std::fabs(z[N - 1]) / std::sqrt(un);
   }
   return true;
 }
+bool ritz_vectors_leading(int dim, const double* alpha, const double* beta, int k, std::vector<double>& WU, std::vector<double>& WV) {
+  std::vector<double> sig, Z;
+  if (!leading_triplets(dim, alpha, beta, k, sig, Z)) return false;
+  const int N = 2 * dim + 1;
+  WU.assign((size_t)(dim + 1) * k, 0.0);
+  WV.assign((size_t)dim * k, 0.0);
+  for (int i = 0; i < k; ++i) {
+    const double* z = Z.data() + (size_t)(k - 1 - i) * N;
+    double un = 0, vn = 0;
+    for (int t = 0; t <= dim; ++t) un += z[2 * t] * z[2 * t];
+    for (int t = 0; t < dim; ++t) vn += z[2 * t + 1] * z[2 * t + 1];
+    if (!(un > 0.25 && un < 0.75 && vn > 0.25 && vn < 0.75)) return false;
+    const double su = 1.0 / std::sqrt(un), sv = 1.0 / std::sqrt(vn);
+    for (int t = 0; t <= dim; ++t) WU[(size_t)i * (dim + 1) + t] = su * z[2 * t];
+    for (int t = 0; t < dim; ++t) WV[(size_t)i * dim + t] = sv * z[2 * t + 1];
+  }
+  return true;
+}
+bool ritz_vectors_leading(int, const float*, const float*, int, std::vector<float>&, std::vector<float>&) { return false; }
 bool ritz_leading(int, const float*, const float*, int, float*, float*) { return false; }
 
 }  // namespace host

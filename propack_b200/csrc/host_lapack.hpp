@@ -3,6 +3,7 @@
 // upstream vendors LAPACK 3.0 under */Lapack_Util, here the image's LAPACK is bound at run time).
 #pragma once
 #include <cstddef>
+#include <vector>
 
 namespace pb {
 namespace host {
@@ -30,6 +31,13 @@ void bdsdc_full(int n, float* d, float* e, float* U, int ldu, float* VT, int ldv
 // caller then takes the reference's xBDSQR route.  The float overload always returns false.
 bool ritz_leading(int j, const double* alpha, const double* beta, int K, double* theta, double* last);
 bool ritz_leading(int j, const float* alpha, const float* beta, int K, float* theta, float* last);
+
+// The k leading singular vector pairs of the same bidiagonal by the same route (dqds + xSTEIN on the Golub-Kahan
+// tridiagonal): WU ((dim+1) x k, leading dimension dim+1) = left vectors u_i, WV (dim x k, ld dim) = right vectors v_i,
+// unit norm, B v_i = sigma_i u_i.  These are the small matrices the Ritz-vector GEMMs multiply the Lanczos bases with
+// (dritzvec.F:116-193 obtains them from dbdqr + dbdsdc of ALL dim vectors).  Same decline conditions as ritz_leading.
+bool ritz_vectors_leading(int dim, const double* alpha, const double* beta, int k, std::vector<double>& WU, std::vector<double>& WV);
+bool ritz_vectors_leading(int dim, const float* alpha, const float* beta, int k, std::vector<float>& WU, std::vector<float>& WV);
 
 }  // namespace host
 }  // namespace pb

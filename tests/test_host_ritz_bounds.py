@@ -78,3 +78,34 @@ def test_fast_route_declines_on_reducible_and_repeated_input():
     alpha[:] = 1.0; beta[:] = 1e-16                  # negligible coupling
     assert _bounds(j, alpha, beta, K, 1)[0] == 1
     assert _bounds(j, alpha, beta, K, 0)[0] == 0     # the reference route always answers
+
+
+def _ritz_w(dim, alpha, beta, k, method):
+    from propack_b200 import _lib
+    L = _lib.lib()
+    WU = np.zeros((dim + 1, k), order="F"); WV = np.zeros((dim, k), order="F")
+    rc = L.propack_b200_host_ritz_vectors_d(C.c_int(dim), _p(np.ascontiguousarray(alpha[:dim])), _p(np.ascontiguousarray(beta[:dim])),
+                                            C.c_int(k), C.c_int(method), _p(WU), _p(WV))
+    return rc, WU, WV
+
+
+@pytest.mark.parametrize("dim,k", [(128, 20), (226, 50), (420, 50), (420, 100)])
+def test_fast_ritz_vector_matrices_are_singular_vectors_of_B(lanczos_bidiagonal, dim, k):
+    """The fast route's WU, WV are the k leading singular vector pairs of the (dim+1) x dim lower bidiagonal: orthonormal,
+    B v = sigma u, B^T u = sigma v to working precision, and equal to the reference route's (dbdqr + dbdsdc) up to sign."""
+    alpha, beta = lanczos_bidiagonal
+    B = np.zeros((dim + 1, dim))
+    B[np.arange(dim), np.arange(dim)] = alpha[:dim]
+    B[np.arange(1, dim + 1), np.arange(dim)] = beta[:dim]
+    s = np.linalg.svd(B, compute_uv=False)[:k]
+    rc0, U0, V0 = _ritz_w(dim, alpha, beta, k, 0)
+    rc1, U1, V1 = _ritz_w(dim, alpha, beta, k, 1)
+    assert rc0 == 0 and rc1 == 0
+    for U, V in ((U0, V0), (U1, V1)):
+        assert np.max(np.abs(U.T @ U - np.eye(k))) < 5e-13 and np.max(np.abs(V.T @ V - np.eye(k))) < 5e-13
+        assert np.max(np.abs(B @ V - U * s)) < 1e-12 * s[0]
+        assert np.max(np.abs(B.T @ U - V * s)) < 1e-12 * s[0]
+    # same vectors up to a common sign per pair (the leading values of this spectrum are distinct)
+    su = np.sign(np.sum(U0 * U1, axis=0))
+    assert np.all(su != 0)
+    assert np.max(np.abs(U1 * su - U0)) < 1e-9 and np.max(np.abs(V1 * su - V0)) < 1e-9
