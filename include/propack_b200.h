@@ -146,6 +146,62 @@ void csgemm_ovwr_left_(const char* transb, const int* m, const int* n, const int
 void zdgemm_ovwr_left_(const char* transb, const int* m, const int* n, const int* k, pb200_complex16* A, const int* lda, const double* B,
                        const int* ldb, pb200_complex16* zwork, const int* lzwork, size_t transb_len);
 
+/* xRITZVEC -- reference double/dritzvec.F:1-2 (args :11-55), single/sritzvec.F; complex16/zritzvec.F:1-2 and
+ * complex8/critzvec.F add (zwork, lzwrk) after in_lwrk.  U(ldu,dim+1), V(ldv,dim) hold the Lanczos bases on entry and the
+ * k Ritz vectors in their first k columns on return; D(dim), E(dim) = diagonal / sub-diagonal of B on entry, D returns
+ * the singular values of B (descending), E is destroyed (dbdqr + dbdsdc, :116-123).  S is not referenced (the
+ * reference never writes it either).  work/iwork are accepted for compatibility. */
+void sritzvec_(const char* which, const char* jobu, const char* jobv, const int* m, const int* n, const int* k, const int* dim,
+               float* D, float* E, float* S, float* U, const int* ldu, float* V, const int* ldv, float* work, const int* in_lwrk,
+               int* iwork, size_t which_len, size_t jobu_len, size_t jobv_len);
+void dritzvec_(const char* which, const char* jobu, const char* jobv, const int* m, const int* n, const int* k, const int* dim,
+               double* D, double* E, double* S, double* U, const int* ldu, double* V, const int* ldv, double* work,
+               const int* in_lwrk, int* iwork, size_t which_len, size_t jobu_len, size_t jobv_len);
+void critzvec_(const char* which, const char* jobu, const char* jobv, const int* m, const int* n, const int* k, const int* dim,
+               float* D, float* E, float* S, pb200_complex8* U, const int* ldu, pb200_complex8* V, const int* ldv, float* work,
+               const int* in_lwrk, pb200_complex8* cwork, const int* lcwrk, int* iwork, size_t which_len, size_t jobu_len,
+               size_t jobv_len);
+void zritzvec_(const char* which, const char* jobu, const char* jobv, const int* m, const int* n, const int* k, const int* dim,
+               double* D, double* E, double* S, pb200_complex16* U, const int* ldu, pb200_complex16* V, const int* ldv,
+               double* work, const int* in_lwrk, pb200_complex16* zwork, const int* lzwrk, int* iwork, size_t which_len,
+               size_t jobu_len, size_t jobv_len);
+
+/* xGEMM_OVWR -- reference double/dgemm_ovwr.F:5-6 (single/sgemm_ovwr.F): B <- alpha*op(A)*B + beta*B, op(A) m x k,
+ * B k x n on entry and m x n on return (ldb >= max(m,k)).  Used by dritzvec on the small (dim+1)-square factors. */
+void sgemm_ovwr_(const char* transa, const int* m, const int* n, const int* k, const float* alpha, const float* A, const int* lda,
+                 const float* beta, float* B, const int* ldb, float* work, const int* lwork, size_t transa_len);
+void dgemm_ovwr_(const char* transa, const int* m, const int* n, const int* k, const double* alpha, const double* A, const int* lda,
+                 const double* beta, double* B, const int* ldb, double* dwork, const int* ldwork, size_t transa_len);
+
+/* blasext level-1 -- reference double/dblasext.F: pdnrm2 :6, pdscal :38, pdaxpy :92, pddot :121, pdzero :202;
+ * complex16/zblasext.F: pdznrm2 :6, pzdscal :60, pzaxpy :113, pzdaxpy :138, pzdotc :167, pzdotu :197, pzzero :344;
+ * single/sblasext.F and complex8/cblasext.F likewise.  Host vectors (any increment) staged through the device kernels
+ * the Lanczos loop uses; complex functions return by value like gfortran's COMPLEX functions. */
+float psnrm2_(const int* n, const float* x, const int* incx);
+double pdnrm2_(const int* n, const double* x, const int* incx);
+float pscnrm2_(const int* n, const pb200_complex8* x, const int* incx);
+double pdznrm2_(const int* n, const pb200_complex16* x, const int* incx);
+float psdot_(const int* n, const float* x, const int* incx, const float* y, const int* incy);
+double pddot_(const int* n, const double* x, const int* incx, const double* y, const int* incy);
+pb200_complex8 pcdotc_(const int* n, const pb200_complex8* x, const int* incx, const pb200_complex8* y, const int* incy);
+pb200_complex16 pzdotc_(const int* n, const pb200_complex16* x, const int* incx, const pb200_complex16* y, const int* incy);
+pb200_complex8 pcdotu_(const int* n, const pb200_complex8* x, const int* incx, const pb200_complex8* y, const int* incy);
+pb200_complex16 pzdotu_(const int* n, const pb200_complex16* x, const int* incx, const pb200_complex16* y, const int* incy);
+void psaxpy_(const int* n, const float* alpha, const float* x, const int* incx, float* y, const int* incy);
+void pdaxpy_(const int* n, const double* alpha, const double* x, const int* incx, double* y, const int* incy);
+void pcaxpy_(const int* n, const pb200_complex8* alpha, const pb200_complex8* x, const int* incx, pb200_complex8* y, const int* incy);
+void pzaxpy_(const int* n, const pb200_complex16* alpha, const pb200_complex16* x, const int* incx, pb200_complex16* y, const int* incy);
+void pcsaxpy_(const int* n, const float* alpha, const pb200_complex8* x, const int* incx, pb200_complex8* y, const int* incy);
+void pzdaxpy_(const int* n, const double* alpha, const pb200_complex16* x, const int* incx, pb200_complex16* y, const int* incy);
+void psscal_(const int* n, const float* alpha, float* x, const int* incx);
+void pdscal_(const int* n, const double* alpha, double* x, const int* incx);
+void pcsscal_(const int* n, const float* alpha, pb200_complex8* x, const int* incx);
+void pzdscal_(const int* n, const double* alpha, pb200_complex16* x, const int* incx);
+void pszero_(const int* n, float* x, const int* incx);
+void pdzero_(const int* n, double* x, const int* incx);
+void pczero_(const int* n, pb200_complex8* x, const int* incx);
+void pzzero_(const int* n, pb200_complex16* x, const int* incx);
+
 /* Host bidiagonal algebra -- reference double/dbsvd.F: dbsvdstep :5, dbdqr :87, drefinebounds :162;
  * omega-recurrence helpers double/dlanbpro.F: dset_mu :555, dcompute_int :581, dupdate_mu :628, dupdate_nu :684. */
 void sbsvdstep_(const char* jobu, const char* jobv, const int* m, const int* n, const int* k, const float* sigma, float* D, float* E,
@@ -189,8 +245,14 @@ int propack_b200_csr_create_c(int m, int n, const int* rowptr, const int* colind
 int propack_b200_csr_create_z(int m, int n, const int* rowptr, const int* colind, const pb200_complex16* values, int index_base);
 /* Copy back the device-built transpose (CSR of A^T, 0-based, sorted) -- integer work is bit-exact and testable. */
 int propack_b200_csr_get_transpose(int handle, int* t_rowptr, int* t_colind, void* t_values);
+/* The SELL-32-sigma copy the default SpMV kernel streams (adjoint = 1: the copy of A^T): info4 = slices, stored entries
+ * incl. padding, sigma (rows per sorting window), long-row threshold; then the arrays themselves (slice_offsets[slices+1],
+ * perm[32*slices] = original row | 0x40000000 for a long row, -1 = no row; colind/values[stored], column -1 = padding). */
+int propack_b200_csr_sell_info(int handle, int adjoint, long long* info4);
+int propack_b200_csr_get_sell(int handle, int adjoint, long long* slice_offsets, int* perm, int* colind, void* values);
 /* Dense column-major m x n operator; host array is copied (…_create) or a device array is adopted, not copied
- * (…_adopt_device; it must stay alive, lda in elements, columns 16-byte aligned). */
+ * (…_adopt_device; it must stay alive; base 16-byte aligned, lda in elements and a multiple of the 128-bit pack (2 doubles),
+ * rows m..lda-1 of every column zero -- the GEMV kernels read whole packs). */
 int propack_b200_dense_create_s(int m, int n, const float* A, long lda);
 int propack_b200_dense_create_d(int m, int n, const double* A, long lda);
 int propack_b200_dense_create_c(int m, int n, const pb200_complex8* A, long lda);
@@ -200,7 +262,7 @@ int propack_b200_dense_adopt_device_d(int m, int n, const double* A_device, long
  * A(i,j) = u(i,j) + sum_g table[g][byte_g(X(i)^Y(j))], see csrc/dense_gen.cu and propack_b200/synth.py (bit-identical
  * numpy replica for parity tests).  Plays the role of the user's APROD data (double/dlansvd.F:20-33). */
 int propack_b200_dense_create_synthetic_d(int m, int n, unsigned long long seed, const double* table16x256);
-int propack_b200_op_destroy(int handle);
+int propack_b200_op_destroy(int handle);   /* drops the handle; solver sessions created on it keep the operator alive */
 /* HBM bytes one product moves by the SURVEY 8(d) model (adjoint = 0: A x, 1: A^H x) */
 double propack_b200_op_bytes(int handle, int adjoint);
 
@@ -262,7 +324,7 @@ int propack_b200_host_ritz_vectors_d(int dim, const double* alpha, const double*
 int propack_b200_init(void);                         /* create the context on the current device; 0 or negative */
 int propack_b200_set_stream(void* cuda_stream);      /* run on a caller stream (e.g. torch's current stream) */
 int propack_b200_set_lapack(const char* path);       /* shared object providing {d,s}bdsqr / {d,s}bdsdc */
-int propack_b200_set_option(const char* name, int value); /* "l2_persist": keep the SpMV's gathered vector L2-resident (default 0: measured slower on config 5) */
+int propack_b200_set_option(const char* name, int value); /* "peer_timeout_s": give up on a silent peer rank after this many seconds (default 30) */
 void propack_b200_set_profile(int on);               /* per-phase CUDA-event timers (adds synchronisation) */
 void propack_b200_reset_counters(void);
 /* out[0..15] = nopx nreorth ndot nitref nrestart nbsvd nlandim nsing nsteps reorth_passes reorth_cols

@@ -221,3 +221,67 @@ def csr_aprod(transa, A, x, dtype=np.float64):
     y = np.zeros(m if transa == "n" else n, dtype=op.dtype)
     getattr(lib(), f"oracle_csr_aprod_{op.sfx}")(C.c_int(ord(transa)), C.c_int(m), C.c_int(n), *op.args()[:6], _p(x), _p(y))
     return y
+
+
+def nrm2(x):
+    """pdnrm2 / pdznrm2 (dblasext.F:6-30, OpenMP branch)."""
+    x = np.ascontiguousarray(x)
+    sfx = _SFX[x.dtype]
+    f = getattr(lib(), f"oracle_nrm2_{sfx}")
+    f.restype = C.c_float if _REAL[sfx] is np.float32 else C.c_double
+    return float(f(C.c_long(x.size), _p(x)))
+
+
+def dotc(x, y):
+    """pddot / pzdotc (dblasext.F:121-147): conj(x).y"""
+    x = np.ascontiguousarray(x); y = np.ascontiguousarray(y, dtype=x.dtype)
+    sfx = _SFX[x.dtype]
+    out = np.zeros(1, dtype=x.dtype)
+    getattr(lib(), f"oracle_dotc_{sfx}")(C.c_long(x.size), _p(x), _p(y), _p(out))
+    return out[0]
+
+
+def axpy(alpha, x, y):
+    """pdaxpy / pzaxpy (dblasext.F:92-115): returns alpha*x + y"""
+    x = np.ascontiguousarray(x); y = np.array(y, dtype=x.dtype, copy=True)
+    sfx = _SFX[x.dtype]
+    a = np.array([alpha], dtype=x.dtype)
+    getattr(lib(), f"oracle_axpy_{sfx}")(C.c_long(x.size), _p(a), _p(x), _p(y))
+    return y
+
+
+def scal(alpha, x):
+    """pdscal / pzdscal (dblasext.F:38-60)"""
+    x = np.array(x, copy=True)
+    sfx = _SFX[x.dtype]
+    getattr(lib(), f"oracle_scal_{sfx}")(C.c_long(x.size), _rc(sfx, alpha), _p(x))
+    return x
+
+
+def ritzvec(which, U, V, D, E, k, jobu=True, jobv=True):
+    """dritzvec (dritzvec.F:1-199).  U (m, dim+1), V (n, dim) Lanczos bases; returns (U[:, :k], V[:, :k], D_out)."""
+    U = np.array(U, order="F", copy=True); V = np.array(V, order="F", copy=True)
+    sfx = _SFX[U.dtype]
+    R = _REAL[sfx]
+    D = np.array(D, dtype=R, copy=True); E = np.array(E, dtype=R, copy=True)
+    dim = D.size
+    getattr(lib(), f"oracle_ritzvec_{sfx}")(C.c_int(ord(which)), C.c_int(int(jobu)), C.c_int(int(jobv)), C.c_int(U.shape[0]),
+                                            C.c_int(V.shape[0]), C.c_int(k), C.c_int(dim), _p(D), _p(E), _p(U),
+                                            C.c_long(U.shape[0]), _p(V), C.c_long(V.shape[0]))
+    return U[:, :k], V[:, :k], D
+
+
+def lanbpro(A, k0, k, U, V, B, rnorm, delta=None, eta=None, anorm=0.0, cgs=False, elr=True, dtype=np.float64):
+    """xLANBPRO (dlanbpro.F:1-549) in place on U (m,k+1), V (n,k), B (k,2).  Returns (k, rnorm, ierr, anorm)."""
+    op = Operator(A, dtype)
+    sfx, R = op.sfx, _REAL[op.sfx]
+    m, n = op.shape
+    eps = np.finfo(R).eps
+    doption = np.array([np.sqrt(eps) if delta is None else delta, eps ** 0.75 if eta is None else eta, anorm], dtype=R)
+    ioption = np.array([int(cgs), int(elr)], dtype=np.int32)
+    kk, ierr = C.c_int(k), C.c_int(0)
+    rn = _rc(sfx, rnorm)
+    getattr(lib(), f"oracle_lanbpro_{sfx}")(C.c_int(m), C.c_int(n), C.c_int(k0), C.byref(kk), *op.args(), _p(U), C.c_long(U.shape[0]),
+                                            _p(V), C.c_long(V.shape[0]), _p(B), C.c_int(B.shape[0]), C.byref(rn), _p(doption),
+                                            _p(ioption), C.byref(ierr))
+    return kk.value, float(rn.value), ierr.value, float(doption[2])

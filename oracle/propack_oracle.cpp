@@ -81,6 +81,13 @@ template <class T> static void op_aprod(char transa, int m, int n, const T* x, T
     gemm_ovwr_left<T>((char)transb, m, n, k, A, lda, B, ldb);                                                         \
   }                                                                                                                   \
   void oracle_safescal_##SFX(long n, R alpha, T* x) { safescal<T>(n, alpha, x); }                                     \
+  void oracle_dotc_##SFX(long n, const T* x, const T* y, T* out) { *out = pdotc<T>(n, x, y); }                        \
+  void oracle_axpy_##SFX(long n, const T* alpha, const T* x, T* y) { paxpy<T, T>(n, *alpha, x, y); }                  \
+  void oracle_scal_##SFX(long n, R alpha, T* x) { pscal<T, R>(n, alpha, x); }                                         \
+  void oracle_ritzvec_##SFX(int which, int jobu, int jobv, int m, int n, int k, int dim, R* D, R* E, T* U, long ldu, \
+                            T* V, long ldv) {                                                                         \
+    ritzvec<T>((char)which, jobu != 0, jobv != 0, m, n, k, dim, D, E, U, ldu, V, ldv);                                \
+  }                                                                                                                   \
   void oracle_csr_aprod_##SFX(int transa, int m, int n, const int* rp, const int* ci, const T* va, const int* trp,   \
                               const int* tci, const T* tva, const T* x, T* y) {                                       \
     CsrOp<T> A{m, n, rp, ci, va, trp, tci, tva};                                                                      \

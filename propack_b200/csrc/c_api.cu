@@ -21,7 +21,7 @@ struct pb200_timing_common timing_;
 
 namespace {
 
-std::string g_last_error;
+thread_local std::string g_last_error;   // per calling thread, like errno
 void set_error(const std::string& s) { g_last_error = s; }
 
 int error_code(const std::exception& e) {
@@ -46,54 +46,46 @@ template <> struct abi<cplx<double>> { using type = pb200_complex16; static cons
 
 struct OpEntry {
   char tag = 0;
-  int kind = 0;  // 0 csr, 1 dense
+  int kind = 0;  // 0 csr, 1 dense, 2 row-sharded csr
   std::shared_ptr<void> op;
 };
 struct SolverEntry {
   char tag = 0;
   int op_handle = 0;
+  std::shared_ptr<void> op;       // keeps the operator alive while the session exists (op_destroy only drops the handle)
   std::shared_ptr<void> engine;
 };
+// Handle tables.  The library is not re-entrant (like the reference: COMMON /timing/, SAVEd variables), but handle
+// creation / destruction may come from different host threads, so the maps themselves are guarded.
+std::mutex g_mu;
 std::map<int, OpEntry> g_ops;
 std::map<int, SolverEntry> g_solvers;
 int g_next_op = 1, g_next_solver = 1;
 
-template <class T> LinOp<T>* lookup_op(int handle) {
+int register_op(const OpEntry& e) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  const int h = g_next_op++;
+  g_ops[h] = e;
+  return h;
+}
+OpEntry find_op(int handle) {
+  std::lock_guard<std::mutex> lk(g_mu);
   auto it = g_ops.find(handle);
   if (it == g_ops.end()) throw std::runtime_error("propack_b200: unknown operator handle " + std::to_string(handle));
-  if (it->second.tag != abi<T>::tag) throw std::runtime_error("propack_b200: operator handle has a different precision");
-  return static_cast<LinOp<T>*>(it->second.op.get());
+  return it->second;
 }
+template <class T> std::shared_ptr<void> lookup_op_shared(int handle) {
+  OpEntry e = find_op(handle);
+  if (e.tag != abi<T>::tag) throw std::runtime_error("propack_b200: operator handle has a different precision");
+  return e.op;
+}
+template <class T> LinOp<T>* lookup_op(int handle) { return static_cast<LinOp<T>*>(lookup_op_shared<T>(handle).get()); }
 
 bool is_yes(const char* c) { return c && (*c == 'y' || *c == 'Y'); }
 
 // ---------------------------------------------------------------------------------------------------
 // CSR registration: upload, device-independent host analysis of row lengths, transpose.
 // ---------------------------------------------------------------------------------------------------
-// rp_host: the row pointers on the host (0-based), or null to fetch them from the device (the transpose's are
-// produced there); used once to list the long rows.
-template <class T> void fill_device_csr(CsrDevice<T>& D, int rows, int cols, long nnz, const DeviceBuffer<int>& rp,
-                                        const DeviceBuffer<int>& ci, const DeviceBuffer<T>& va, const int* rp_host, int rp_base,
-                                        DeviceBuffer<int>& long_rows) {
-  D.rows = rows; D.cols = cols; D.nnz = nnz; D.rp = rp.p; D.ci = ci.p; D.va = va.p;
-  std::vector<int> tmp;
-  if (!rp_host) {
-    tmp.resize((size_t)rows + 1);
-    PB_CUDA(cudaMemcpy(tmp.data(), rp.p, sizeof(int) * ((size_t)rows + 1), cudaMemcpyDeviceToHost));
-    rp_host = tmp.data(); rp_base = 0;
-  }
-  (void)rp_base;  // differences of row pointers do not depend on the index base
-  const std::vector<int> lr = csr_long_rows(rp_host, rows, spmv_group_nnz<T>());
-  D.n_long = (int)lr.size();
-  if (D.n_long) {
-    long_rows.alloc(lr.size());
-    PB_CUDA(cudaMemcpy(long_rows.p, lr.data(), sizeof(int) * lr.size(), cudaMemcpyHostToDevice));
-    D.long_rows = long_rows.p;
-  }
-  D.lpr_log2 = csr_lanes_per_row_log2(nnz, rows, spmv_group_nnz<T>());
-  if (const char* e = std::getenv("PROPACK_B200_SPMV_LPR_LOG2")) D.lpr_log2 = std::min(5, std::max(0, std::atoi(e)));
-}
-
 template <class T> int csr_create(int m, int n, const int* rowptr, const int* colind, const void* values_, int base) {
   PB_API_TRY
   Context& c = Context::get();
@@ -105,8 +97,8 @@ template <class T> int csr_create(int m, int n, const int* rowptr, const int* co
   op->m = m; op->n = n;
   op->rp.alloc(m + 1); op->ci.alloc(std::max<long>(nnz, 1)); op->va.alloc(std::max<long>(nnz, 1));
   op->trp.alloc(n + 1); op->tci.alloc(std::max<long>(nnz, 1)); op->tva.alloc(std::max<long>(nnz, 1));
-  // the three host arrays go up as they are; re-basing, validation (column range, sorted rows) and the canonical
-  // transpose run on the device (csr_build.cu)
+  // the three host arrays go up as they are; re-basing, validation (row pointers, column range, sorted rows), the
+  // canonical transpose and the SELL copies are all built on the device (csr_build.cu, sell.cu)
   PB_CUDA(cudaMemcpyAsync(op->rp.p, rowptr, sizeof(int) * (m + 1), cudaMemcpyHostToDevice, c.stream));
   if (nnz) {
     PB_CUDA(cudaMemcpyAsync(op->ci.p, colind, sizeof(int) * nnz, cudaMemcpyHostToDevice, c.stream));
@@ -114,15 +106,14 @@ template <class T> int csr_create(int m, int n, const int* rowptr, const int* co
   }
   k_rebase(c, m + 1, op->rp.p, base);
   k_rebase(c, nnz, op->ci.p, base);
+  if (k_csr_check_rowptr(c, m, nnz, op->rp.p)) throw std::runtime_error("propack_b200: CSR row pointers must be non-decreasing");
   const int st = k_csr_transpose<T>(c, m, n, nnz, op->rp.p, op->ci.p, op->va.p, op->trp.p, op->tci.p, op->tva.p);
   if (st & 2) throw std::runtime_error("propack_b200: CSR column index out of range");
   if (st & 1) throw std::runtime_error("propack_b200: CSR column indices must be sorted within each row");
-  fill_device_csr<T>(op->A, m, n, nnz, op->rp, op->ci, op->va, rowptr, base, op->lrows);
-  fill_device_csr<T>(op->At, n, m, nnz, op->trp, op->tci, op->tva, nullptr, 0, op->tlrows);
+  finish_operand<T>(c, op->A, m, n, nnz, op->rp.p, op->ci.p, op->va.p);
+  finish_operand<T>(c, op->At, n, m, nnz, op->trp.p, op->tci.p, op->tva.p);
   OpEntry e; e.tag = abi<T>::tag; e.kind = 0; e.op = op;
-  const int h = g_next_op++;
-  g_ops[h] = e;
-  return h;
+  return register_op(e);
   PB_API_CATCH(return code__)
 }
 
@@ -133,7 +124,7 @@ template <class T>
 int csr_create_sharded(int mg, int ng, const int* row_rp, const int* row_ci, const void* row_va_, const int* colt_rp,
                        const int* colt_ci, const void* colt_va_, int base) {
   PB_API_TRY
-  Context::get();
+  Context& c = Context::get();
   Comm& cm = Comm::get();
   const T* row_va = static_cast<const T*>(row_va_);
   const T* colt_va = static_cast<const T*>(colt_va_);
@@ -146,77 +137,48 @@ int csr_create_sharded(int mg, int ng, const int* row_rp, const int* row_ci, con
   op->m = ml; op->n = nl; op->mg = mg; op->ng = ng; op->m_off = r0; op->n_off = c0;
   op->ld_m = shard_slice(mg, cm.world); op->ld_n = shard_slice(ng, cm.world);
   op->sharded = true;
-  // number of column groups (sub-SpMVs per product), must divide world; 1 unless PROPACK_B200_SPMV_GROUPS says
-  // otherwise (the grouped, chunk-pipelined product is an experiment that measured slower: see ShardedCsrOperator)
-  int G = 1;
-  if (const char* e = std::getenv("PROPACK_B200_SPMV_GROUPS")) G = std::max(1, std::atoi(e));
-  G = std::min(G, cm.world);
+  // phases (sub-products gated on the arrival of their source slices) per product: must divide world
+  int G = std::min(cm.world, 4);
+  if (const char* e = std::getenv("PROPACK_B200_SPMV_PHASES")) G = std::max(1, std::atoi(e));
+  G = std::min(std::min(G, cm.world), 8);
   while (cm.world % G) --G;
+  // The shard goes up as it is; validation, the split into phases and the SELL copies are built on the device.
   auto upload = [&](int d, int rows, long width, long ld, const int* rp_in, const int* ci_in, const T* va_in) {
-    const long nnz = (long)rp_in[rows] - rp_in[0];
     if (rp_in[0] != base) throw std::runtime_error("propack_b200: sharded CSR row pointers must start at the index base");
-    const int P = cm.world, per = P / G;
-    auto group_of = [&](int col) {   // ring distance of the owner of `col` behind this rank -> group
-      const int owner = (int)(col / ld);
-      const int dist = ((cm.rank - owner) % P + P) % P;
-      return dist / per;
-    };
-    // pass 1: validate, count per (group, row)
-    std::vector<std::vector<int>> grp(G, std::vector<int>((size_t)rows + 1, 0));
-    for (int i = 0; i < rows; ++i) {
-      int prevc = -1;
-      for (long p = rp_in[i] - base; p < rp_in[i + 1] - base; ++p) {
-        const int col = ci_in[p] - base;
-        if (col < 0 || col >= width) throw std::runtime_error("propack_b200: sharded CSR index out of range");
-        if (col < prevc) throw std::runtime_error("propack_b200: CSR indices must be sorted within each row");
-        prevc = col;
-        grp[group_of(col)][i + 1] += 1;
-      }
+    const long nnz = (long)rp_in[rows] - base;
+    if (nnz < 0) throw std::runtime_error("propack_b200: bad sharded CSR row pointers");
+    DeviceBuffer<int> rp((size_t)rows + 1), ci((size_t)std::max<long>(nnz, 1));
+    DeviceBuffer<T> va((size_t)std::max<long>(nnz, 1));
+    PB_CUDA(cudaMemcpyAsync(rp.p, rp_in, sizeof(int) * ((size_t)rows + 1), cudaMemcpyHostToDevice, c.stream));
+    if (nnz) {
+      PB_CUDA(cudaMemcpyAsync(ci.p, ci_in, sizeof(int) * nnz, cudaMemcpyHostToDevice, c.stream));
+      PB_CUDA(cudaMemcpyAsync(va.p, va_in, sizeof(T) * nnz, cudaMemcpyHostToDevice, c.stream));
     }
-    std::vector<long> goff(G + 1, 0);
+    k_rebase(c, (long)rows + 1, rp.p, base);
+    k_rebase(c, nnz, ci.p, base);
+    if (k_csr_check_rowptr(c, rows, nnz, rp.p)) throw std::runtime_error("propack_b200: sharded CSR row pointers must be non-decreasing");
+    auto& P = op->phases[d];
+    P.clear();
+    std::vector<int*> out_rp(G);
+    std::vector<DeviceBuffer<int>*> out_ci(G);
+    std::vector<DeviceBuffer<T>*> out_va(G);
+    std::vector<long> nnz_g(G, 0);
     for (int g = 0; g < G; ++g) {
-      for (int i = 0; i < rows; ++i) grp[g][i + 1] += grp[g][i];
-      goff[g + 1] = goff[g] + grp[g][rows];
+      P.emplace_back(new typename ShardedCsrOperator<T>::Phase());
+      P[g]->rp.alloc((size_t)rows + 1);
+      out_rp[g] = P[g]->rp.p; out_ci[g] = &P[g]->ci; out_va[g] = &P[g]->va;
     }
-    // pass 2: scatter into the group-major arrays (columns stay ascending inside a row)
-    std::vector<int> hci(std::max<long>(nnz, 1));
-    std::vector<T> hva(std::max<long>(nnz, 1));
-    std::vector<std::vector<int>> next(G);
-    for (int g = 0; g < G; ++g) next[g].assign(grp[g].begin(), grp[g].end() - 1);
-    for (int i = 0; i < rows; ++i)
-      for (long p = rp_in[i] - base; p < rp_in[i + 1] - base; ++p) {
-        const int col = ci_in[p] - base, g = group_of(col);
-        const long q = goff[g] + next[g][i]++;
-        hci[q] = col; hva[q] = va_in[p];
-      }
-    std::vector<int> hrp((size_t)G * (rows + 1)), hlong;
-    std::vector<int> long_off(G + 1, 0);
+    const int st = k_csr_split_phases<T>(c, rows, width, rp.p, ci.p, va.p, ld, cm.world, cm.rank, G, out_rp.data(), out_ci.data(),
+                                         out_va.data(), nnz_g.data());
+    if (st & 2) throw std::runtime_error("propack_b200: sharded CSR index out of range");
+    if (st & 1) throw std::runtime_error("propack_b200: CSR indices must be sorted within each row");
+    const int per = cm.world / G;
     for (int g = 0; g < G; ++g) {
-      std::copy(grp[g].begin(), grp[g].end(), hrp.begin() + (size_t)g * (rows + 1));
-      const std::vector<int> lr = csr_long_rows(grp[g].data(), rows, spmv_group_nnz<T>());
-      hlong.insert(hlong.end(), lr.begin(), lr.end());
-      long_off[g + 1] = (int)hlong.size();
-    }
-    op->rp_all[d].alloc(hrp.size()); op->ci_all[d].alloc(hci.size()); op->va_all[d].alloc(hva.size());
-    op->long_all[d].alloc(std::max<size_t>(hlong.size(), 1));
-    PB_CUDA(cudaMemcpy(op->rp_all[d].p, hrp.data(), sizeof(int) * hrp.size(), cudaMemcpyHostToDevice));
-    PB_CUDA(cudaMemcpy(op->ci_all[d].p, hci.data(), sizeof(int) * hci.size(), cudaMemcpyHostToDevice));
-    PB_CUDA(cudaMemcpy(op->va_all[d].p, hva.data(), sizeof(T) * hva.size(), cudaMemcpyHostToDevice));
-    if (!hlong.empty()) PB_CUDA(cudaMemcpy(op->long_all[d].p, hlong.data(), sizeof(int) * hlong.size(), cudaMemcpyHostToDevice));
-    op->groups[d].resize(G);
-    for (int g = 0; g < G; ++g) {
-      auto& Gr = op->groups[d][g];
-      Gr.M.rows = rows; Gr.M.cols = (int)(ld * P); Gr.M.nnz = goff[g + 1] - goff[g];
-      Gr.M.rp = op->rp_all[d].p + (size_t)g * (rows + 1);
-      Gr.M.ci = op->ci_all[d].p + goff[g];
-      Gr.M.va = op->va_all[d].p + goff[g];
-      Gr.M.lpr_log2 = csr_lanes_per_row_log2(Gr.M.nnz, rows, spmv_group_nnz<T>());
-      Gr.M.n_long = long_off[g + 1] - long_off[g];
-      Gr.M.long_rows = Gr.M.n_long ? op->long_all[d].p + long_off[g] : nullptr;
-      Gr.src_mask = 0;
+      finish_operand<T>(c, P[g]->S, rows, (int)(ld * cm.world), nnz_g[g], P[g]->rp.p, P[g]->ci.p, P[g]->va.p);
+      P[g]->src_mask = 0;
       for (int k = g * per; k < (g + 1) * per; ++k) {
-        const int src = ((cm.rank - k) % P + P) % P;
-        if (src != cm.rank) Gr.src_mask |= 1u << src;
+        const int src = ((cm.rank - k) % cm.world + cm.world) % cm.world;
+        if (src != cm.rank) P[g]->src_mask |= 1u << src;
       }
     }
   };
@@ -224,9 +186,7 @@ int csr_create_sharded(int mg, int ng, const int* row_rp, const int* row_ci, con
   upload(1, nl, mg, op->ld_m, colt_rp, colt_ci, colt_va);
   op->alloc_gather_buffers();
   OpEntry e; e.tag = abi<T>::tag; e.kind = 2; e.op = op;
-  const int h = g_next_op++;
-  g_ops[h] = e;
-  return h;
+  return register_op(e);
   PB_API_CATCH(return code__)
 }
 
@@ -235,7 +195,14 @@ template <class T> int dense_create(int m, int n, const void* A_, long lda, bool
   Context& c = Context::get();
   auto op = std::make_shared<DenseOperator<T>>();
   op->m = m; op->n = n;
+  if (m <= 0 || n <= 0 || !A_ || lda < m) throw std::runtime_error("propack_b200: bad dense operator arguments");
   if (adopt_device) {
+    // the GEMV kernels read whole 128-bit packs: columns must be 16-byte aligned and the rows m..lda-1 of every column
+    // (the padding up to the pack boundary) must be zero -- the caller owns the buffer, so only the layout is checked
+    constexpr int VEC = 16 / (int)sizeof(T);
+    if (lda % VEC != 0 || (reinterpret_cast<uintptr_t>(A_) & 15u) != 0 || (m % VEC != 0 && lda < (m + VEC - 1) / VEC * VEC))
+      throw std::runtime_error("propack_b200: adopted dense operator needs a 16-byte aligned base, lda a multiple of the 128-bit pack "
+                               "and zeroed padding rows up to the pack boundary");
     op->A = static_cast<const T*>(A_); op->lda = lda;
   } else {
     const long ld = Engine<T>::pad_ld(m);
@@ -246,9 +213,7 @@ template <class T> int dense_create(int m, int n, const void* A_, long lda, bool
     op->A = op->store.p; op->lda = ld;
   }
   OpEntry e; e.tag = abi<T>::tag; e.kind = 1; e.op = op;
-  const int h = g_next_op++;
-  g_ops[h] = e;
-  return h;
+  return register_op(e);
   PB_API_CATCH(return code__)
 }
 
@@ -263,11 +228,13 @@ template <> void* builtin_aprod<cplx<double>>() { return (void*)&propack_b200_ap
 
 template <class T> struct ResolvedOp {
   LinOp<T>* op = nullptr;
+  std::shared_ptr<void> keep;
   CallbackOperator<T> cb;
   ResolvedOp(void* aprod, int m, int n, void* parm, int* iparm) {
     if (aprod == builtin_aprod<T>()) {
       if (!iparm) throw std::runtime_error("propack_b200: built-in APROD needs the operator handle in iparm(1)");
-      op = lookup_op<T>(iparm[0]);
+      keep = lookup_op_shared<T>(iparm[0]);
+      op = static_cast<LinOp<T>*>(keep.get());
       if (op->m != m || op->n != n) throw std::runtime_error("propack_b200: m,n do not match the registered operator");
     } else {
       if (!aprod) throw std::runtime_error("propack_b200: APROD is null");
@@ -436,10 +403,149 @@ void gemm_ovwr_left_entry(const char* transb, int m, int n, int k, real_t<T> alp
   PB_API_CATCH(return )
 }
 
+// dritzvec (dritzvec.F:1-199; complex: zritzvec.F:1-2): U(:,1:k) <- U(:,1:dim+1) X^T, V(:,1:k) <- V(:,1:dim) Q with the
+// small factors from dbdqr + dbdsdc of the bidiagonal (D, E) -- the reference route, so D returns the singular values
+// of B in descending order and E is destroyed, as in the Fortran.
+template <class T>
+void ritzvec_entry(const char* which, const char* jobu, const char* jobv, int m, int n, int k, int dim, real_t<T>* D, real_t<T>* E,
+                   real_t<T>* S, void* U, int ldu, void* V, int ldv) {
+  PB_API_TRY
+  if (k <= 0 || dim <= 0 || m <= 0 || n <= 0) return;
+  Context& c = Context::get();
+  NullOp<T> nop; nop.m = m; nop.n = n;
+  Engine<T> eng(c, &nop, dim + 1, dim);
+  const bool ju = is_yes(jobu), jv = is_yes(jobv);
+  const bool smallest = which && (*which == 's' || *which == 'S');
+  if (ju) upload_cols<T>(c, eng.U, eng.ldu, U, ldu, m, dim + 1);
+  if (jv) upload_cols<T>(c, eng.V, eng.ldv, V, ldv, n, dim);
+  eng.ritzvec(smallest, ju, jv, k, dim, D, E, /*reference_route=*/true);
+  if (ju) download_cols<T>(c, U, ldu, eng.U, eng.ldu, m, k);
+  if (jv) download_cols<T>(c, V, ldv, eng.V, eng.ldv, n, k);
+  c.sync();
+  (void)S;   // documented as output in dritzvec.F:26-28 but never written by the reference either; D carries the values
+  publish_timing(c);
+  PB_API_CATCH(fprintf(stderr, "%s\n", g_last_error.c_str()))
+}
+
+// dgemm_ovwr (dgemm_ovwr.F:5-53): B(m x n) <- alpha*op(A)*B + beta*B, op(A) m x k, B k x n on entry (ldb >= max(m,k)).
+// The product runs through the tall-GEMM kernel on the transposed problem  B^T (n x k) * op(A)^T (k x m).
+template <class R>
+void gemm_ovwr_entry(const char* transa, int m, int n, int k, R alpha, const R* A, int lda, R beta, R* B, int ldb) {
+  PB_API_TRY
+  if (m <= 0 || n <= 0 || k <= 0) return;
+  if (m > ldb) throw std::runtime_error("propack_b200: m>ldb in xGEMM_OVWR");
+  Context& c = Context::get();
+  const bool tr = transa && (*transa == 't' || *transa == 'T');
+  std::vector<R> W((size_t)k * m);        // W(l, i) = alpha * op(A)(i, l)
+  for (int i = 0; i < m; ++i)
+    for (int l = 0; l < k; ++l) W[(size_t)i * k + l] = alpha * (tr ? A[(size_t)i * lda + l] : A[(size_t)l * lda + i]);
+  std::vector<R> Bt((size_t)n * k);       // B^T, n x k column-major
+  for (int l = 0; l < k; ++l)
+    for (int j = 0; j < n; ++j) Bt[(size_t)l * n + j] = B[(size_t)j * ldb + l];
+  NullOp<R> nop; nop.m = n; nop.n = 1;
+  Engine<R> eng(c, &nop, std::max(k, m), 1);
+  upload_cols<R>(c, eng.U, eng.ldu, Bt.data(), n, n, k);
+  k_gemm_tall<R>(c, n, m, k, eng.U, eng.ldu, W.data());
+  std::vector<R> Ct((size_t)n * m);
+  download_cols<R>(c, Ct.data(), n, eng.U, eng.ldu, n, m);
+  c.sync();
+  for (int j = 0; j < n; ++j)
+    for (int i = 0; i < m; ++i) {
+      const R v = Ct[(size_t)i * n + j];
+      B[(size_t)j * ldb + i] = beta == R(0) ? v : v + beta * B[(size_t)j * ldb + i];
+    }
+  PB_API_CATCH(fprintf(stderr, "%s\n", g_last_error.c_str()))
+}
+
+// ---- blasext level-1 (dblasext.F:6-255, zblasext.F): host vectors staged through the device kernels -----------------
+template <class T> struct HostVec {   // strided host vector -> padded device vector (and back)
+  DeviceBuffer<T> d;
+  std::vector<T> packed;
+  long n;
+  HostVec(Context& c, long n_, const void* x, int incx) : n(n_) {
+    d.alloc((size_t)Engine<T>::pad_ld(std::max<long>(n, 1)));
+    PB_CUDA(cudaMemsetAsync(d.p, 0, sizeof(T) * d.n, c.stream));
+    if (n <= 0 || !x) return;
+    const T* xs = static_cast<const T*>(x);
+    if (incx == 1) { PB_CUDA(cudaMemcpyAsync(d.p, xs, sizeof(T) * n, cudaMemcpyHostToDevice, c.stream)); return; }
+    packed.resize(n);
+    const long start = incx < 0 ? (long)(1 - n) * incx : 0;   // BLAS convention for negative increments
+    for (long i = 0; i < n; ++i) packed[i] = xs[start + i * incx];
+    PB_CUDA(cudaMemcpyAsync(d.p, packed.data(), sizeof(T) * n, cudaMemcpyHostToDevice, c.stream));
+  }
+  void store(Context& c, void* x, int incx) {
+    if (n <= 0) return;
+    T* xs = static_cast<T*>(x);
+    if (incx == 1) { PB_CUDA(cudaMemcpyAsync(xs, d.p, sizeof(T) * n, cudaMemcpyDeviceToHost, c.stream)); c.sync(); return; }
+    packed.resize(n);
+    PB_CUDA(cudaMemcpyAsync(packed.data(), d.p, sizeof(T) * n, cudaMemcpyDeviceToHost, c.stream));
+    c.sync();
+    const long start = incx < 0 ? (long)(1 - n) * incx : 0;
+    for (long i = 0; i < n; ++i) xs[start + i * incx] = packed[i];
+  }
+};
+template <class T> real_t<T> l1_nrm2(int n, const void* x, int incx) {
+  PB_API_TRY
+  if (n <= 0) return 0;
+  Context& c = Context::get();
+  HostVec<T> hx(c, n, x, incx);
+  Pending p; k_nrm2<T>(c, n, hx.d.p, &p);
+  return (real_t<T>)c.wait(p);
+  PB_API_CATCH(return real_t<T>(-1))
+}
+template <class T> void l1_dot(int n, const void* x, int incx, const void* y, int incy, bool conj, double* re, double* im) {
+  *re = *im = 0;
+  PB_API_TRY
+  if (n <= 0) return;
+  Context& c = Context::get();
+  HostVec<T> hx(c, n, x, incx), hy(c, n, y, incy);
+  Pending p; k_dotc<T>(c, n, hx.d.p, hy.d.p, &p);
+  *re = c.wait(p, im);
+  if (!conj && scalar_traits<T>::is_complex) {   // x.y = conj(conj(x).conj(y)): unconjugated product via the conjugated vector
+    std::vector<T> xc(n);
+    const T* xs = static_cast<const T*>(x);
+    const long start = incx < 0 ? (long)(1 - n) * incx : 0;
+    for (long i = 0; i < n; ++i) xc[i] = conj_(xs[start + i * incx]);
+    HostVec<T> hc(c, n, xc.data(), 1);
+    Pending q; k_dotc<T>(c, n, hc.d.p, hy.d.p, &q);
+    *re = c.wait(q, im);
+  }
+  PB_API_CATCH(return )
+}
+template <class T> void l1_axpy(int n, T alpha, const void* x, int incx, void* y, int incy) {
+  PB_API_TRY
+  if (n <= 0) return;
+  Context& c = Context::get();
+  HostVec<T> hx(c, n, x, incx), hy(c, n, y, incy);
+  Pending p; k_axpy_nrm<T>(c, n, alpha, hx.d.p, hy.d.p, &p);
+  c.wait(p);
+  hy.store(c, y, incy);
+  PB_API_CATCH(return )
+}
+template <class T> void l1_scal(int n, real_t<T> alpha, void* x, int incx) {
+  PB_API_TRY
+  if (n <= 0) return;
+  Context& c = Context::get();
+  HostVec<T> hx(c, n, x, incx);
+  k_scal<T>(c, n, hx.d.p, alpha);
+  hx.store(c, x, incx);
+  PB_API_CATCH(return )
+}
+template <class T> void l1_zero(int n, void* x, int incx) {
+  PB_API_TRY
+  if (n <= 0) return;
+  Context& c = Context::get();
+  HostVec<T> hx(c, n, x, incx);
+  k_zero<T>(c, n, hx.d.p);
+  hx.store(c, x, incx);
+  PB_API_CATCH(return )
+}
+
 template <class T> void aprod_entry(const char* transa, int m, int n, const void* x, void* y, int* iparm) {
   PB_API_TRY
   Context& c = Context::get();
-  LinOp<T>* op = lookup_op<T>(iparm[0]);
+  std::shared_ptr<void> keep = lookup_op_shared<T>(iparm[0]);
+  LinOp<T>* op = static_cast<LinOp<T>*>(keep.get());
   const bool adjoint = !(transa && (*transa == 'n' || *transa == 'N'));
   const long nx = adjoint ? m : n, ny = adjoint ? n : m;
   DeviceBuffer<T> dx(Engine<T>::pad_ld(nx)), dy(Engine<T>::pad_ld(ny));
@@ -457,15 +563,17 @@ template <class T> void aprod_entry(const char* transa, int m, int n, const void
 // ---------------------------------------------------------------------------------------------------
 template <class T> int solver_create_t(int op_handle, int ucols, int vcols) {
   Context& c = Context::get();
-  LinOp<T>* op = lookup_op<T>(op_handle);
-  auto eng = std::make_shared<Engine<T>>(c, op, ucols, vcols);
-  SolverEntry e; e.tag = abi<T>::tag; e.op_handle = op_handle; e.engine = eng;
+  std::shared_ptr<void> keep = lookup_op_shared<T>(op_handle);
+  auto eng = std::make_shared<Engine<T>>(c, static_cast<LinOp<T>*>(keep.get()), ucols, vcols);
+  SolverEntry e; e.tag = abi<T>::tag; e.op_handle = op_handle; e.op = keep; e.engine = eng;
+  c.sync();
+  std::lock_guard<std::mutex> lk(g_mu);
   const int id = g_next_solver++;
   g_solvers[id] = e;
-  c.sync();
   return id;
 }
-SolverEntry& find_solver(int id) {
+SolverEntry find_solver(int id) {
+  std::lock_guard<std::mutex> lk(g_mu);
   auto it = g_solvers.find(id);
   if (it == g_solvers.end()) throw std::runtime_error("propack_b200: unknown solver id");
   return it->second;
@@ -580,6 +688,77 @@ PB_COMMON(d, double, double, double, pb200_aprod_d_t)
 PB_COMMON(c, cplx<float>, float, pb200_complex8, pb200_aprod_c_t)
 PB_COMMON(z, cplx<double>, double, pb200_complex16, pb200_aprod_z_t)
 
+// ---- xRITZVEC (dritzvec.F:1-2; zritzvec.F:1-2 adds zwork, lzwrk) and xGEMM_OVWR (dgemm_ovwr.F:5) ---------------------------
+#define PB_RITZ_REAL(P, T, R)                                                                                                   \
+  void P##ritzvec_(const char* which, const char* jobu, const char* jobv, const int* m, const int* n, const int* k,            \
+                   const int* dim, R* D, R* E, R* S, R* U, const int* ldu, R* V, const int* ldv, R* work, const int* in_lwrk,  \
+                   int* iwork, size_t, size_t, size_t) {                                                                        \
+    (void)work; (void)in_lwrk; (void)iwork;                                                                                     \
+    ritzvec_entry<T>(which, jobu, jobv, *m, *n, *k, *dim, D, E, S, U, *ldu, V, *ldv);                                           \
+  }                                                                                                                             \
+  void P##gemm_ovwr_(const char* transa, const int* m, const int* n, const int* k, const R* alpha, const R* A, const int* lda, \
+                     const R* beta, R* B, const int* ldb, R* dwork, const int* ldwork, size_t) {                                \
+    (void)dwork; (void)ldwork;                                                                                                  \
+    gemm_ovwr_entry<R>(transa, *m, *n, *k, *alpha, A, *lda, *beta, B, *ldb);                                                    \
+  }
+#define PB_RITZ_CPLX(P, T, R, CT)                                                                                               \
+  void P##ritzvec_(const char* which, const char* jobu, const char* jobv, const int* m, const int* n, const int* k,            \
+                   const int* dim, R* D, R* E, R* S, CT* U, const int* ldu, CT* V, const int* ldv, R* work, const int* in_lwrk, \
+                   CT* zwork, const int* lzwrk, int* iwork, size_t, size_t, size_t) {                                           \
+    (void)work; (void)in_lwrk; (void)zwork; (void)lzwrk; (void)iwork;                                                           \
+    ritzvec_entry<T>(which, jobu, jobv, *m, *n, *k, *dim, D, E, S, U, *ldu, V, *ldv);                                           \
+  }
+PB_RITZ_REAL(s, float, float)
+PB_RITZ_REAL(d, double, double)
+PB_RITZ_CPLX(c, cplx<float>, float, pb200_complex8)
+PB_RITZ_CPLX(z, cplx<double>, double, pb200_complex16)
+
+// ---- blasext level-1 (dblasext.F:6,38,92,121,202; zblasext.F:6,60,113,167,344; s/c likewise) --------------------------------
+float psnrm2_(const int* n, const float* x, const int* incx) { return l1_nrm2<float>(*n, x, *incx); }
+double pdnrm2_(const int* n, const double* x, const int* incx) { return l1_nrm2<double>(*n, x, *incx); }
+float pscnrm2_(const int* n, const pb200_complex8* x, const int* incx) { return l1_nrm2<cplx<float>>(*n, x, *incx); }
+double pdznrm2_(const int* n, const pb200_complex16* x, const int* incx) { return l1_nrm2<cplx<double>>(*n, x, *incx); }
+float psdot_(const int* n, const float* x, const int* incx, const float* y, const int* incy) {
+  double re, im; l1_dot<float>(*n, x, *incx, y, *incy, true, &re, &im); return (float)re;
+}
+double pddot_(const int* n, const double* x, const int* incx, const double* y, const int* incy) {
+  double re, im; l1_dot<double>(*n, x, *incx, y, *incy, true, &re, &im); return re;
+}
+pb200_complex8 pcdotc_(const int* n, const pb200_complex8* x, const int* incx, const pb200_complex8* y, const int* incy) {
+  double re, im; l1_dot<cplx<float>>(*n, x, *incx, y, *incy, true, &re, &im); return pb200_complex8{(float)re, (float)im};
+}
+pb200_complex16 pzdotc_(const int* n, const pb200_complex16* x, const int* incx, const pb200_complex16* y, const int* incy) {
+  double re, im; l1_dot<cplx<double>>(*n, x, *incx, y, *incy, true, &re, &im); return pb200_complex16{re, im};
+}
+pb200_complex8 pcdotu_(const int* n, const pb200_complex8* x, const int* incx, const pb200_complex8* y, const int* incy) {
+  double re, im; l1_dot<cplx<float>>(*n, x, *incx, y, *incy, false, &re, &im); return pb200_complex8{(float)re, (float)im};
+}
+pb200_complex16 pzdotu_(const int* n, const pb200_complex16* x, const int* incx, const pb200_complex16* y, const int* incy) {
+  double re, im; l1_dot<cplx<double>>(*n, x, *incx, y, *incy, false, &re, &im); return pb200_complex16{re, im};
+}
+void psaxpy_(const int* n, const float* a, const float* x, const int* incx, float* y, const int* incy) { l1_axpy<float>(*n, *a, x, *incx, y, *incy); }
+void pdaxpy_(const int* n, const double* a, const double* x, const int* incx, double* y, const int* incy) { l1_axpy<double>(*n, *a, x, *incx, y, *incy); }
+void pcaxpy_(const int* n, const pb200_complex8* a, const pb200_complex8* x, const int* incx, pb200_complex8* y, const int* incy) {
+  l1_axpy<cplx<float>>(*n, cplx<float>(a->re, a->im), x, *incx, y, *incy);
+}
+void pzaxpy_(const int* n, const pb200_complex16* a, const pb200_complex16* x, const int* incx, pb200_complex16* y, const int* incy) {
+  l1_axpy<cplx<double>>(*n, cplx<double>(a->re, a->im), x, *incx, y, *incy);
+}
+void pcsaxpy_(const int* n, const float* a, const pb200_complex8* x, const int* incx, pb200_complex8* y, const int* incy) {
+  l1_axpy<cplx<float>>(*n, cplx<float>(*a, 0.f), x, *incx, y, *incy);
+}
+void pzdaxpy_(const int* n, const double* a, const pb200_complex16* x, const int* incx, pb200_complex16* y, const int* incy) {
+  l1_axpy<cplx<double>>(*n, cplx<double>(*a, 0.0), x, *incx, y, *incy);
+}
+void psscal_(const int* n, const float* a, float* x, const int* incx) { l1_scal<float>(*n, *a, x, *incx); }
+void pdscal_(const int* n, const double* a, double* x, const int* incx) { l1_scal<double>(*n, *a, x, *incx); }
+void pcsscal_(const int* n, const float* a, pb200_complex8* x, const int* incx) { l1_scal<cplx<float>>(*n, *a, x, *incx); }
+void pzdscal_(const int* n, const double* a, pb200_complex16* x, const int* incx) { l1_scal<cplx<double>>(*n, *a, x, *incx); }
+void pszero_(const int* n, float* x, const int* incx) { l1_zero<float>(*n, x, *incx); }
+void pdzero_(const int* n, double* x, const int* incx) { l1_zero<double>(*n, x, *incx); }
+void pczero_(const int* n, pb200_complex8* x, const int* incx) { l1_zero<cplx<float>>(*n, x, *incx); }
+void pzzero_(const int* n, pb200_complex16* x, const int* incx) { l1_zero<cplx<double>>(*n, x, *incx); }
+
 // ---- host bidiagonal algebra (real only, as in the reference) -------------------------------------------
 #define PB_HOST_ALG(P, R)                                                                                                       \
   void P##bsvdstep_(const char* jobu, const char* jobv, const int* m, const int* n, const int* k, const R* sigma, R* D, R* E,    \
@@ -662,31 +841,76 @@ int propack_b200_dense_create_synthetic_d(int m, int n, unsigned long long seed,
   k_dense_synth(c, m, n, ld, seed, table16x256, op->store.p);
   op->A = op->store.p; op->lda = ld;
   OpEntry e; e.tag = 'd'; e.kind = 1; e.op = op;
-  const int h = g_next_op++;
-  g_ops[h] = e;
-  return h;
+  return register_op(e);
   PB_API_CATCH(return code__)
 }
-int propack_b200_op_destroy(int handle) { return g_ops.erase(handle) ? 0 : -1; }
+// Drops the handle.  Solver sessions created on the operator keep it alive until they are destroyed themselves.
+int propack_b200_op_destroy(int handle) {
+  std::shared_ptr<void> last;   // the operator (device memory, peer windows) is released outside the lock
+  {
+    std::lock_guard<std::mutex> lk(g_mu);
+    auto it = g_ops.find(handle);
+    if (it == g_ops.end()) return -1;
+    last = it->second.op;
+    g_ops.erase(it);
+  }
+  return 0;
+}
 double propack_b200_op_bytes(int handle, int adjoint) {
-  auto it = g_ops.find(handle);
-  if (it == g_ops.end()) return -1.0;
-  return dispatch(it->second.tag, [&](auto* t) {
-    using T = std::remove_pointer_t<decltype(t)>;
-    return static_cast<LinOp<T>*>(it->second.op.get())->algorithmic_bytes(adjoint != 0);
-  });
+  try {
+    OpEntry e = find_op(handle);
+    return dispatch(e.tag, [&](auto* t) {
+      using T = std::remove_pointer_t<decltype(t)>;
+      return static_cast<LinOp<T>*>(e.op.get())->algorithmic_bytes(adjoint != 0);
+    });
+  } catch (...) { return -1.0; }
 }
 int propack_b200_csr_get_transpose(int handle, int* t_rowptr, int* t_colind, void* t_values) {
   PB_API_TRY
-  auto it = g_ops.find(handle);
-  if (it == g_ops.end() || it->second.kind != 0) throw std::runtime_error("propack_b200: not a CSR operator handle");
-  return dispatch(it->second.tag, [&](auto* t) {
+  OpEntry e = find_op(handle);
+  if (e.kind != 0) throw std::runtime_error("propack_b200: not a CSR operator handle");
+  return dispatch(e.tag, [&](auto* t) {
     using T = std::remove_pointer_t<decltype(t)>;
-    auto* op = static_cast<CsrOperator<T>*>(it->second.op.get());
+    auto* op = static_cast<CsrOperator<T>*>(e.op.get());
     PB_CUDA(cudaMemcpy(t_rowptr, op->trp.p, sizeof(int) * (op->n + 1), cudaMemcpyDeviceToHost));
-    if (op->A.nnz) {
-      PB_CUDA(cudaMemcpy(t_colind, op->tci.p, sizeof(int) * op->A.nnz, cudaMemcpyDeviceToHost));
-      PB_CUDA(cudaMemcpy(t_values, op->tva.p, sizeof(T) * op->A.nnz, cudaMemcpyDeviceToHost));
+    if (op->A.csr.nnz) {
+      PB_CUDA(cudaMemcpy(t_colind, op->tci.p, sizeof(int) * op->A.csr.nnz, cudaMemcpyDeviceToHost));
+      PB_CUDA(cudaMemcpy(t_values, op->tva.p, sizeof(T) * op->A.csr.nnz, cudaMemcpyDeviceToHost));
+    }
+    return 0;
+  });
+  PB_API_CATCH(return code__)
+}
+
+// SELL-32-sigma copy of a registered CSR operator (adjoint = 1: of A^T): sizes, then the arrays (integer work, bit-exact
+// against the numpy restatement in tests/sell_ref.py).  info[0..3] = slices, stored entries incl. padding, sigma, long-row threshold.
+int propack_b200_csr_sell_info(int handle, int adjoint, long long* info4) {
+  PB_API_TRY
+  OpEntry e = find_op(handle);
+  if (e.kind != 0) throw std::runtime_error("propack_b200: not a CSR operator handle");
+  return dispatch(e.tag, [&](auto* t) {
+    using T = std::remove_pointer_t<decltype(t)>;
+    auto* op = static_cast<CsrOperator<T>*>(e.op.get());
+    const SellDevice<T>& S = (adjoint ? op->At : op->A).sell.dev;
+    info4[0] = S.nslices; info4[1] = S.padded; info4[2] = kSellSigma; info4[3] = kSellLong;
+    return 0;
+  });
+  PB_API_CATCH(return code__)
+}
+int propack_b200_csr_get_sell(int handle, int adjoint, long long* slice_offsets, int* perm, int* colind, void* values) {
+  PB_API_TRY
+  OpEntry e = find_op(handle);
+  if (e.kind != 0) throw std::runtime_error("propack_b200: not a CSR operator handle");
+  return dispatch(e.tag, [&](auto* t) {
+    using T = std::remove_pointer_t<decltype(t)>;
+    auto* op = static_cast<CsrOperator<T>*>(e.op.get());
+    const SellDevice<T>& S = (adjoint ? op->At : op->A).sell.dev;
+    if (S.soff == nullptr) throw std::runtime_error("propack_b200: the operator has no SELL copy (PROPACK_B200_SPMV=csr)");
+    PB_CUDA(cudaMemcpy(slice_offsets, S.soff, sizeof(long long) * (S.nslices + 1), cudaMemcpyDeviceToHost));
+    PB_CUDA(cudaMemcpy(perm, S.perm, sizeof(int) * S.nslices * 32, cudaMemcpyDeviceToHost));
+    if (S.padded) {
+      PB_CUDA(cudaMemcpy(colind, S.ci, sizeof(int) * S.padded, cudaMemcpyDeviceToHost));
+      PB_CUDA(cudaMemcpy(values, S.va, sizeof(T) * S.padded, cudaMemcpyDeviceToHost));
     }
     return 0;
   });
@@ -696,18 +920,27 @@ int propack_b200_csr_get_transpose(int handle, int* t_rowptr, int* t_colind, voi
 // ---- solver sessions ----------------------------------------------------------------------------------------
 int propack_b200_solver_create(int op_handle, int ucols, int vcols) {
   PB_API_TRY
-  auto it = g_ops.find(op_handle);
-  if (it == g_ops.end()) throw std::runtime_error("propack_b200: unknown operator handle");
-  return dispatch(it->second.tag, [&](auto* t) {
+  OpEntry e = find_op(op_handle);
+  return dispatch(e.tag, [&](auto* t) {
     using T = std::remove_pointer_t<decltype(t)>;
     return solver_create_t<T>(op_handle, ucols, vcols);
   });
   PB_API_CATCH(return code__)
 }
-int propack_b200_solver_destroy(int solver) { return g_solvers.erase(solver) ? 0 : -1; }
+int propack_b200_solver_destroy(int solver) {
+  SolverEntry last;   // engine buffers are freed outside the lock
+  {
+    std::lock_guard<std::mutex> lk(g_mu);
+    auto it = g_solvers.find(solver);
+    if (it == g_solvers.end()) return -1;
+    last = it->second;
+    g_solvers.erase(it);
+  }
+  return 0;
+}
 int propack_b200_solver_set_start(int solver, const void* u0_host) {
   PB_API_TRY
-  SolverEntry& s = find_solver(solver);
+  SolverEntry s = find_solver(solver);
   return dispatch(s.tag, [&](auto* t) {
     using T = std::remove_pointer_t<decltype(t)>;
     auto* e = static_cast<Engine<T>*>(s.engine.get());
@@ -721,7 +954,7 @@ int propack_b200_solver_set_start(int solver, const void* u0_host) {
 int propack_b200_solver_lansvd(int solver, int jobu, int jobv, int* k, int kmax, void* sigma, void* bnd, double tolin, void* option3,
                                int* ioption, int* info) {
   PB_API_TRY
-  SolverEntry& s = find_solver(solver);
+  SolverEntry s = find_solver(solver);
   return dispatch(s.tag, [&](auto* t) {
     using T = std::remove_pointer_t<decltype(t)>;
     using R = real_t<T>;
@@ -736,7 +969,7 @@ int propack_b200_solver_lansvd(int solver, int jobu, int jobv, int* k, int kmax,
 int propack_b200_solver_lansvd_irl(int solver, int which_smallest, int jobu, int jobv, int* dim, int p, int* neig, int maxiter,
                                    void* sigma, void* bnd, double tolin, void* option4, int* ioption, int* info) {
   PB_API_TRY
-  SolverEntry& s = find_solver(solver);
+  SolverEntry s = find_solver(solver);
   return dispatch(s.tag, [&](auto* t) {
     using T = std::remove_pointer_t<decltype(t)>;
     using R = real_t<T>;
@@ -751,7 +984,7 @@ int propack_b200_solver_lansvd_irl(int solver, int which_smallest, int jobu, int
 }
 int propack_b200_solver_get_u(int solver, int ncols, void* U_host, long ldu) {
   PB_API_TRY
-  SolverEntry& s = find_solver(solver);
+  SolverEntry s = find_solver(solver);
   return dispatch(s.tag, [&](auto* t) {
     using T = std::remove_pointer_t<decltype(t)>;
     auto* e = static_cast<Engine<T>*>(s.engine.get());
@@ -763,7 +996,7 @@ int propack_b200_solver_get_u(int solver, int ncols, void* U_host, long ldu) {
 }
 int propack_b200_solver_get_v(int solver, int ncols, void* V_host, long ldv) {
   PB_API_TRY
-  SolverEntry& s = find_solver(solver);
+  SolverEntry s = find_solver(solver);
   return dispatch(s.tag, [&](auto* t) {
     using T = std::remove_pointer_t<decltype(t)>;
     auto* e = static_cast<Engine<T>*>(s.engine.get());
@@ -789,6 +1022,7 @@ int propack_b200_comm_init(int rank, int world, const void* id128) {
   c.peer_table = cm.peer_ok ? cm.slots.table_dev : nullptr;
   c.coef_table = cm.peer_ok ? cm.coef.table_dev : nullptr;
   c.peer_rank = cm.rank; c.peer_world = cm.world;
+  c.reset_peer_counters();   // collective call: every rank restarts the (slot, sequence) matching of the fused reductions
   return 0;
   PB_API_CATCH(return code__)
 }
@@ -811,7 +1045,7 @@ void propack_b200_comm_stats(long long* n_allreduce, long long* n_allgather, dou
 }
 int propack_b200_solver_local_rows(int solver, int* m_local, int* n_local, long* ldu, long* ldv) {
   PB_API_TRY
-  SolverEntry& s = find_solver(solver);
+  SolverEntry s = find_solver(solver);
   return dispatch(s.tag, [&](auto* t) {
     using T = std::remove_pointer_t<decltype(t)>;
     auto* e = static_cast<Engine<T>*>(s.engine.get());
@@ -880,7 +1114,7 @@ int propack_b200_set_option(const char* name, int value) {
   PB_API_TRY
   Context& c = Context::get();
   const std::string n = name ? name : "";
-  if (n == "l2_persist") { c.l2_persist = value != 0; c.set_l2_window(nullptr, 0); return 0; }
+  if (n == "peer_timeout_s") { c.set_peer_timeout(value); return 0; }
   throw std::runtime_error("propack_b200: unknown option '" + n + "'");
   PB_API_CATCH(return code__)
 }
@@ -959,11 +1193,10 @@ double propack_b200_bench_reorth_d(long L, int l, int reps, int flush_l2) {
 double propack_b200_bench_spmv(int op_handle, int adjoint, int reps, int flush_l2) {
   PB_API_TRY
   Context& c = Context::get();
-  auto it = g_ops.find(op_handle);
-  if (it == g_ops.end()) throw std::runtime_error("propack_b200: unknown operator handle");
-  return dispatch(it->second.tag, [&](auto* t) {
+  OpEntry e = find_op(op_handle);
+  return dispatch(e.tag, [&](auto* t) {
     using T = std::remove_pointer_t<decltype(t)>;
-    LinOp<T>* op = static_cast<LinOp<T>*>(it->second.op.get());
+    LinOp<T>* op = static_cast<LinOp<T>*>(e.op.get());
     const long nx = adjoint ? op->m : op->n, ny = adjoint ? op->n : op->m;
     DeviceBuffer<T> x(Engine<T>::pad_ld(nx)), y(Engine<T>::pad_ld(ny)), prev(Engine<T>::pad_ld(ny));
     PB_CUDA(cudaMemsetAsync(x.p, 0, sizeof(T) * x.n, c.stream));

@@ -176,6 +176,7 @@ struct ReduceWs {              // workspace of one in-flight grid reduction
   void** peer_table;           // device array: peer_table[r] = rank r's PeerSlot window, or null
   int rank, world, slot;
   volatile unsigned int* host_err;  // mapped pinned error word (set when a peer never shows up)
+  long long timeout_cycles;         // give up on a peer after this many SM clocks (do not hang the GPU)
 };
 
 struct PeerSlotDev {           // layout of comm.hpp::PeerSlot
@@ -225,7 +226,7 @@ __device__ inline void grid_publish(double vre, double vim, const ReduceWs& ws, 
       for (int q = 0; q < ws.world; ++q) {
         PeerSlotDev* m = static_cast<PeerSlotDev*>(ws.peer_table[ws.rank]) + q * kPeerSlotsPerRank + ws.slot;
         while (*reinterpret_cast<volatile unsigned long long*>(&m->seq) != ws.seq) {
-          if (clock64() - t0 > 20000000000LL) { dead = true; break; }   // ~10 s: a peer died; do not hang the GPU
+          if (clock64() - t0 > ws.timeout_cycles) { dead = true; break; }   // a peer died; do not hang the GPU
         }
         if (dead) break;
         __threadfence();

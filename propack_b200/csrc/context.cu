@@ -31,11 +31,6 @@ Context::Context() {
   PB_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
   PB_CUDA(cudaStreamCreateWithFlags(&stream2, cudaStreamNonBlocking));
   PB_CUDA(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
-  l2_persist_max = (size_t)prop.persistingL2CacheMaxSize;
-  l2_window_max = (size_t)prop.accessPolicyMaxWindowSize;
-  // (the persisting set-aside is only carved out of L2 when the experiment is switched on: reserving it
-  // unconditionally cost 15% on the SpMV and 2x on the level-1 kernels, whose operands otherwise hit in L2)
-  if (const char* e = std::getenv("PROPACK_B200_L2_PERSIST")) l2_persist = e[0] != '0';
   PB_CUDA(cudaHostAlloc((void**)&host_slots, sizeof(ScalarSlot) * kSlots, cudaHostAllocMapped));
   std::memset((void*)host_slots, 0, sizeof(ScalarSlot) * kSlots);
   PB_CUDA(cudaHostGetDevicePointer((void**)&host_slots_dev, (void*)host_slots, 0));
@@ -51,29 +46,7 @@ Context::Context() {
   PB_CUDA(cudaMemset(tickets8, 0, sizeof(unsigned int) * 8));
   PB_CUDA(cudaDeviceSynchronize());
   profile = std::getenv("PROPACK_B200_PROFILE") != nullptr;
-}
-
-void Context::set_l2_window(const void* p, size_t bytes) {
-  if (!l2_persist || l2_persist_max == 0 || bytes < (16u << 20)) {
-    if (l2_win_ptr) {   // drop a stale window
-      cudaStreamAttrValue a{};
-      a.accessPolicyWindow.num_bytes = 0;
-      cudaStreamSetAttribute(stream, cudaStreamAttributeAccessPolicyWindow, &a);
-      l2_win_ptr = nullptr; l2_win_bytes = 0;
-    }
-    return;
-  }
-  if (p == l2_win_ptr && bytes == l2_win_bytes) return;
-  if (!l2_limit_set) { cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, l2_persist_max); l2_limit_set = true; }
-  cudaStreamAttrValue a{};
-  const size_t nb = bytes < l2_window_max ? bytes : l2_window_max;
-  a.accessPolicyWindow.base_ptr = const_cast<void*>(p);
-  a.accessPolicyWindow.num_bytes = nb;
-  a.accessPolicyWindow.hitRatio = nb <= l2_persist_max ? 1.0f : (float)((double)l2_persist_max / (double)nb);
-  a.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
-  a.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
-  PB_CUDA(cudaStreamSetAttribute(stream, cudaStreamAttributeAccessPolicyWindow, &a));
-  l2_win_ptr = p; l2_win_bytes = bytes;
+  if (const char* e = std::getenv("PROPACK_B200_PEER_TIMEOUT_S")) set_peer_timeout(std::atoi(e));
 }
 
 void Context::set_stream(cudaStream_t s) {
@@ -81,7 +54,6 @@ void Context::set_stream(cudaStream_t s) {
   if (owns_stream && stream) cudaStreamDestroy(stream);
   stream = s;
   owns_stream = false;
-  l2_win_ptr = nullptr; l2_win_bytes = 0;
 }
 
 double Context::wait(const Pending& p, double* imag) {

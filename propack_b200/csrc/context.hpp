@@ -29,7 +29,7 @@ class Context {
  public:
   static Context& get();       // lazily created on the current device
   cudaStream_t stream = nullptr;
-  cudaStream_t stream2 = nullptr;       // side stream: the NVLink push of the chunk-pipelined sharded SpMV runs here
+  cudaStream_t stream2 = nullptr;       // side stream: the NVLink push of a row-sharded SpMV input runs here
   cudaEvent_t ev_fork = nullptr;        // main stream -> side stream dependency
   bool owns_stream = true;
   int device = 0;
@@ -52,17 +52,32 @@ class Context {
   // Row-sharded runs (one process per GPU): while set, every reduction a kernel publishes is this rank's partial
   // and is completed across ranks (Comm all-reduce) before the host sees it.  Set by Engine for sharded operators.
   bool dist_reduce = false;
+  // The fused cross-rank reductions match peers by (slot, sequence number), so the counters they use must advance in
+  // lock step on every rank: they are separate from the single-GPU counters (a rank may run extra local work, e.g. a
+  // validation solve on rank 0 only), use their own half of the slot table, and are reset by comm_init on all ranks.
+  static constexpr int kLocalSlots = kSlots / 2;
+  unsigned long long peer_seq = 0;
+  int peer_next_slot = 0;
+  long long peer_timeout_cycles = 60000000000LL;   // ~30 s at 1.9 GHz; PROPACK_B200_PEER_TIMEOUT_S / set_option("peer_timeout_s")
+  void set_peer_timeout(int seconds) { peer_timeout_cycles = (long long)(seconds > 0 ? seconds : 1) * 2000000000LL; }
+  void reset_peer_counters() { peer_seq = 0; peer_next_slot = 0; coef_seq = 0; }
   // Allocate a result slot for the next reducing kernel.
   ReduceWs new_reduce(Pending* p) {
-    int s = next_slot; next_slot = (next_slot + 1) % kSlots;
     ReduceWs ws;
     ws.partials = partials; ws.ticket = ticket;
-    ws.dev_slot = dev_slots + s; ws.host_slot = host_slots_dev + s; ws.seq = ++seq;
-    ws.peer_table = nullptr; ws.rank = 0; ws.world = 1; ws.slot = s; ws.host_err = host_err_dev;
+    ws.peer_table = nullptr; ws.rank = 0; ws.world = 1; ws.host_err = host_err_dev;
+    ws.timeout_cycles = peer_timeout_cycles;
     ws.local_only = dist_reduce ? 1 : 0;
+    int s;
     if (dist_reduce && peer_table) {   // fused path: the kernel itself completes the cross-rank reduction
+      s = kLocalSlots + peer_next_slot; peer_next_slot = (peer_next_slot + 1) % (kSlots - kLocalSlots);
+      ws.seq = ++peer_seq;
       ws.peer_table = peer_table; ws.rank = peer_rank; ws.world = peer_world; ws.local_only = 0;
+    } else {
+      s = next_slot; next_slot = (next_slot + 1) % kLocalSlots;
+      ws.seq = ++seq;
     }
+    ws.dev_slot = dev_slots + s; ws.host_slot = host_slots_dev + s; ws.slot = s;
     p->slot = s; p->seq = ws.seq; p->local_only = ws.local_only;
     return ws;
   }
@@ -79,15 +94,6 @@ class Context {
   // Spin until the kernel that owns `p` has published; returns the real part (imag via out param).
   double wait(const Pending& p, double* imag = nullptr);
 
-  // Optional L2 residency hint for the vector a gather-SpMV reads at random (x): an access-policy window with the
-  // "persisting" hit property.  Measured on config 5 (x = 80 MB): 832 us with the window vs 763 us without -- the
-  // set-aside hurts the streamed operands more than it helps x -- so it is OFF by default (PROPACK_B200_L2_PERSIST=1 or
-  // propack_b200_set_option("l2_persist", 1) to experiment).
-  bool l2_persist = false;
-  bool l2_limit_set = false;
-  size_t l2_persist_max = 0, l2_window_max = 0;
-  const void* l2_win_ptr = nullptr; size_t l2_win_bytes = 0;
-  void set_l2_window(const void* p, size_t bytes);
   void set_stream(cudaStream_t s);
   void sync() { PB_CUDA(cudaStreamSynchronize(stream)); PB_CUDA(cudaStreamSynchronize(stream2)); }
   int grid_for(long work_items, int per_cta, int ctas_per_sm) const {

@@ -61,44 +61,73 @@ template <class T> struct LinOp {
   virtual void invalidate_staged() {}
 };
 
-template <class T> struct CsrOperator : LinOp<T> {
-  using R = real_t<T>;
-  DeviceBuffer<int> rp, ci, trp, tci, lrows, tlrows;
-  DeviceBuffer<T> va, tva;
-  CsrDevice<T> A, At;  // At = CSR of A^T (values not conjugated)
-  void apply(Context& c, bool adjoint, const T* x, T* y, R coef, const T* prev, Pending* nrm) override {
-    if (adjoint) k_spmv<T>(c, At, /*conj=*/true, x, y, coef, prev, nrm);
-    else k_spmv<T>(c, A, false, x, y, coef, prev, nrm);
-  }
-  double algorithmic_bytes(bool adjoint) const override {
-    const double w = sizeof(T);
-    const double rows = adjoint ? this->n : this->m, cols = adjoint ? this->m : this->n;
-    return (double)A.nnz * (w + 4) + (rows + 1) * 4 + cols * w + rows * w;
-  }
+// One sparse operand in its two device forms: the caller's CSR (kept: the long-row kernel and the transpose export read
+// it; PROPACK_B200_SPMV=csr also runs the whole product from it) and the SELL-32-sigma copy the default kernel streams.
+template <class T> struct SparseOperand {
+  CsrDevice<T> csr;
+  SellStorage<T> sell;
+  DeviceBuffer<int> long_rows;
 };
 
-// Row-sharded CSR operator: this rank holds the CSR of its row block of A (m_loc x ng) and the CSR of the transpose
-// of its column block (n_loc x mg), so BOTH products are "all-gather the input vector, then a local gather-SpMV":
-// no cross-rank summation inside a matvec, and every output element is produced by the same kernel in the same
-// order as on one GPU.  Slices are contiguous and of equal padded length, so global column indices address the
-// gathered vector directly.
+inline bool spmv_use_sell() {
+  static const bool on = [] { const char* e = std::getenv("PROPACK_B200_SPMV"); return !(e && (e[0] == 'c' || e[0] == 'C')); }();
+  return on;
+}
+
+// CSR arrays already on the device (0-based, validated) -> long-row list, lanes-per-row of the CSR kernel, SELL copy
+template <class T>
+void finish_operand(Context& c, SparseOperand<T>& S, int rows, int cols, long nnz, const int* rp, const int* ci, const T* va) {
+  CsrDevice<T>& D = S.csr;
+  D.rows = rows; D.cols = cols; D.nnz = nnz; D.rp = rp; D.ci = ci; D.va = va;
+  const bool sell = spmv_use_sell();
+  D.n_long = k_csr_long_rows(c, rows, rp, sell ? kSellLong : spmv_group_nnz<T>() / 2, S.long_rows);
+  D.long_rows = D.n_long ? S.long_rows.p : nullptr;
+  D.lpr_log2 = csr_lanes_per_row_log2(nnz, rows, spmv_group_nnz<T>());
+  if (const char* e = std::getenv("PROPACK_B200_SPMV_LPR_LOG2")) D.lpr_log2 = std::min(5, std::max(0, std::atoi(e)));
+  if (sell) sell_build<T>(c, rows, cols, nnz, rp, ci, va, S.sell);
+}
+
+template <class T> double operand_bytes(const SparseOperand<T>& S) {   // SURVEY 8d byte model of one product (x counted once)
+  const double w = sizeof(T);
+  return (double)S.csr.nnz * (w + 4) + ((double)S.csr.rows + 1) * 4 + (double)S.csr.cols * w + (double)S.csr.rows * w;
+}
+
+template <class T> struct CsrOperator : LinOp<T> {
+  using R = real_t<T>;
+  DeviceBuffer<int> rp, ci, trp, tci;
+  DeviceBuffer<T> va, tva;
+  SparseOperand<T> A, At;  // At = A^T (values not conjugated)
+  void apply(Context& c, bool adjoint, const T* x, T* y, R coef, const T* prev, Pending* nrm) override {
+    SparseOperand<T>& S = adjoint ? At : A;
+    if (spmv_use_sell())
+      k_spmv_sell<T>(c, S.sell.dev, &S.csr, /*conj=*/adjoint, x, y, coef, prev, nrm, kSellModeFinal, nullptr, 0u, 0ull);
+    else
+      k_spmv<T>(c, S.csr, /*conj=*/adjoint, x, y, coef, prev, nrm);
+  }
+  double algorithmic_bytes(bool adjoint) const override { return operand_bytes(adjoint ? At : A); }
+};
+
+// Row-sharded CSR operator: this rank holds its row block of A (m_loc x ng) and the transpose of its column block
+// (n_loc x mg), so BOTH products are "all-gather the input vector, then a local gather-SpMV": no cross-rank summation
+// inside a matvec.  Slices are contiguous and of equal padded length, so global column indices address the gathered
+// vector directly.
+//
+// Each local operand is split by the SOURCE RANK of the gathered vector into G phases (G = min(world, 4) by default,
+// PROPACK_B200_SPMV_PHASES): phase g holds the entries whose column belongs to the ranks at ring distance
+// [g*P/G, (g+1)*P/G) behind this rank -- the order in which the staggered push (k_scal_push) delivers the slices.
+// The product is  y = sum_g A_g x_g : phase g waits, inside its SELL kernel, only for its own sources, so the SpMV over
+// the slices that have landed overlaps the NVLink transfer of the ones still in flight.  The push runs on a few CTAs
+// of a side stream; the SpMV kernels leave it room (k_spmv_sell).
 template <class T> struct ShardedCsrOperator : LinOp<T> {
   using R = real_t<T>;
-  // Each local operand (direction 0: rows of A for A x; direction 1: rows of (A[:, cols])^T for A^H x) is stored as G
-  // column groups (G = 1 by default: one local SpMV, every output element summed in the same order as on one GPU).
-  // G > 1 (PROPACK_B200_SPMV_GROUPS) is the chunk-pipelining experiment: group g holds the entries whose column belongs
-  // to the ranks at ring distance [g*P/G, (g+1)*P/G) behind this rank -- the order in which a staggered push delivers
-  // the slices -- and the product becomes G sub-SpMVs  y = A_g x_g + y  gated on their own slices.  Measured on config 5
-  // at 8 GPUs it LOSES (1.13 s at G=1, 1.15 / 1.25 / 1.47 s at G=2/4/8): the sub-SpMVs' shorter rows cost more than
-  // they hide, because this rank's own push runs on the same stream ahead of them; overlapping needs the push on a
-  // concurrent stream (next step).
-  struct Group {
-    CsrDevice<T> M;
-    unsigned int src_mask = 0;   // ranks whose slices this group reads (own rank excluded: no wait needed)
+  struct Phase {
+    DeviceBuffer<int> rp, ci;
+    DeviceBuffer<T> va;
+    SparseOperand<T> S;
+    unsigned int src_mask = 0;   // ranks whose slices this phase reads (own rank excluded: no wait needed)
   };
-  std::vector<Group> groups[2];
-  DeviceBuffer<int> rp_all[2], ci_all[2], long_all[2];
-  DeviceBuffer<T> va_all[2], xbuf[2];
+  std::vector<std::unique_ptr<Phase>> phases[2];
+  DeviceBuffer<T> xbuf[2];
   // gather buffers: [world*ld elements | kMaxRanks arrival flags]; peer windows when NVLink peer memory is mapped
   // (index 0: the n-vector gathered for A x, index 1: the m-vector gathered for A^H x)
   T* xfull[2] = {nullptr, nullptr};
@@ -133,7 +162,7 @@ template <class T> struct ShardedCsrOperator : LinOp<T> {
     Comm& cm = Comm::get();
     epoch[d] += 1;
     k_scal_push<T>(c, adjoint ? this->m : this->n, ld_of(d), x, scale, win[d].table_dev, cm.rank, cm.world, epoch[d],
-                   /*staggered=*/groups[d].size() > 1, xfull[d] + (size_t)cm.rank * ld_of(d));
+                   xfull[d] + (size_t)cm.rank * ld_of(d));
     staged_ptr[d] = x; staged_valid[d] = true;
     return true;
   }
@@ -141,23 +170,31 @@ template <class T> struct ShardedCsrOperator : LinOp<T> {
   void apply(Context& c, bool adjoint, const T* x, T* y, R coef, const T* prev, Pending* nrm) override {
     Comm& cm = Comm::get();
     const int d = adjoint ? 1 : 0;
-    // staged: the slices are being pushed by the producers (stage_scaled); each group waits only for its own sources.
+    // staged: the slices are being pushed by the producers (stage_scaled); each phase waits only for its own sources.
     // (nrm != nullptr: the cross-rank norm reduction that follows is what makes reusing the buffer safe.)
     const bool staged = staged_valid[d] && staged_ptr[d] == x && nrm != nullptr;
     if (!staged) cm.allgather(x, xfull[d], sizeof(T) * (size_t)ld_of(d), c.stream);
     staged_valid[d] = false;
-    const size_t G = groups[d].size();
+    const size_t G = phases[d].size();
     for (size_t g = 0; g < G; ++g) {
-      if (staged) k_wait_flags(c, flags(d), groups[d][g].src_mask, epoch[d]);
-      k_spmv<T>(c, groups[d][g].M, /*conj=*/adjoint, xfull[d], y, g == 0 ? coef : R(1), g == 0 ? prev : y,
-                g + 1 == G ? nrm : nullptr);
+      Phase& ph = *phases[d][g];
+      const unsigned int mask = staged ? ph.src_mask : 0u;
+      const int mode = (g ? kSellModeAcc : 0) | (g + 1 == G ? kSellModeFinal : 0);
+      if (spmv_use_sell()) {
+        if (mask && ph.S.csr.n_long > 0) k_wait_flags(c, flags(d), mask, epoch[d]);   // the long-row kernel has no in-kernel wait
+        k_spmv_sell<T>(c, ph.S.sell.dev, &ph.S.csr, /*conj=*/adjoint, xfull[d], y, coef, prev, g + 1 == G ? nrm : nullptr, mode,
+                       flags(d), mask, epoch[d]);
+      } else {
+        if (mask) k_wait_flags(c, flags(d), mask, epoch[d]);
+        k_spmv<T>(c, ph.S.csr, /*conj=*/adjoint, xfull[d], y, g == 0 ? coef : R(1), g == 0 ? prev : y, g + 1 == G ? nrm : nullptr);
+      }
     }
   }
   double algorithmic_bytes(bool adjoint) const override {
     const double w = sizeof(T);
     double b = 0;
-    for (const Group& g : groups[adjoint ? 1 : 0])
-      b += (double)g.M.nnz * (w + 4) + ((double)g.M.rows + 1) * 4 + (double)g.M.rows * w;
+    for (const auto& ph : phases[adjoint ? 1 : 0])
+      b += (double)ph->S.csr.nnz * (w + 4) + ((double)ph->S.csr.rows + 1) * 4 + (double)ph->S.csr.rows * w;
     return b + (double)ld_of(adjoint ? 1 : 0) * Comm::get().world * w;
   }
 };
@@ -371,7 +408,7 @@ template <class T> class Engine {
   int lanbpro(int k0, int& k, R* a, R* b, R& rnorm, R* doption, const int* ioption);
 
   // --- dritzvec (dritzvec.F:1-199) -------------------------------------------------------------------------
-  void ritzvec(bool smallest, bool jobu, bool jobv, int k, int dim, R* D, R* E);
+  void ritzvec(bool smallest, bool jobu, bool jobv, int k, int dim, R* D, R* E, bool reference_route = false);
 
   // --- drivers ------------------------------------------------------------------------------------------
   // dlansvd (dlansvd.F:1-291); U(:,1) on device holds the start vector (zero => random).  Returns info.

@@ -246,14 +246,14 @@ void ritz_w_reference(bool ignorelast, bool smallest, bool want_u, bool want_v, 
   }
 }
 
-template <class T> void Engine<T>::ritzvec(bool smallest, bool jobu, bool jobv, int k, int dim, R* D, R* E) {
+template <class T> void Engine<T>::ritzvec(bool smallest, bool jobu, bool jobv, int k, int dim, R* D, R* E, bool reference_route) {
   Context::PhaseScope ps(c, PH_RITZ);
   DistScope ds(c, dist);
   std::vector<R> WU, WV;
   // Large Krylov dimension, largest triplets: the k leading singular vector pairs of B directly (dqds + inverse iteration
   // on the Golub-Kahan tridiagonal) instead of a divide & conquer SVD of all dim pairs; the reference route is the fallback.
   bool fast = false;
-  if (fast_ritz_bounds() && !smallest && dim >= 128 && dim != std::min(mg, ng) && k < dim)
+  if (!reference_route && fast_ritz_bounds() && !smallest && dim >= 128 && dim != std::min(mg, ng) && k < dim)
     fast = host::ritz_vectors_leading(dim, D, E, k, WU, WV);
   if (!fast) ritz_w_reference<R>(dim == std::min(mg, ng), smallest, jobu, jobv, k, dim, D, E, WU, WV);
   if (jobu) k_gemm_tall<T>(c, m, k, dim + 1, U, ldu, WU.data());

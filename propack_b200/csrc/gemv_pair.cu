@@ -152,7 +152,7 @@ gemv_t_finalize(int l, int G, const T* __restrict__ part, int lpad, T* __restric
 template <class T>
 __global__ void __launch_bounds__(kThreads)
 gemv_t_finalize_fused(int l, int G, const T* __restrict__ part, int lpad, T* __restrict__ h, void** bases, int rank, int world,
-                      int buf, unsigned long long seq, unsigned int* ticket, volatile unsigned int* host_err) {
+                      int buf, unsigned long long seq, unsigned int* ticket, volatile unsigned int* host_err, long long timeout_cycles) {
   __shared__ T sm[8][33];
   __shared__ bool is_last;
   constexpr size_t kBuf = (size_t)Comm::kMaxRanks * Comm::kCoefMax * 16;
@@ -183,7 +183,7 @@ gemv_t_finalize_fused(int l, int G, const T* __restrict__ part, int lpad, T* __r
     const unsigned long long* mine = reinterpret_cast<const unsigned long long*>(static_cast<char*>(bases[rank]) + 2 * kBuf);
     const long long t0 = clock64();
     while (*reinterpret_cast<const volatile unsigned long long*>(mine + buf * Comm::kMaxRanks + threadIdx.x) != seq) {
-      if (clock64() - t0 > 20000000000LL) { *host_err = 1u; break; }   // ~10 s: a peer died; do not hang the GPU
+      if (clock64() - t0 > timeout_cycles) { *host_err = 1u; break; }   // a peer died; do not hang the GPU
     }
   }
   __syncthreads();
@@ -309,7 +309,7 @@ template <class T> void k_gemv_t(Context& c, long L, int l, const T* V, long ldv
     // fused: finalize + cross-rank all-reduce of the coefficients over NVLink peer memory, one launch
     c.coef_seq += 1;
     gemv_t_finalize_fused<T><<<ceil_div(l, 32), kThreads, 0, c.stream>>>(l, gx, part, lpad, h, c.coef_table, c.peer_rank, c.peer_world,
-                                                                         (int)(c.coef_seq & 1ull), c.coef_seq, c.ticket, c.host_err_dev);
+                                                                         (int)(c.coef_seq & 1ull), c.coef_seq, c.ticket, c.host_err_dev, c.peer_timeout_cycles);
     PB_LAUNCH_CHECK();
   } else {
     gemv_t_finalize<T><<<ceil_div(l, 32), kThreads, 0, c.stream>>>(l, gx, part, lpad, h);

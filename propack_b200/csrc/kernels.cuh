@@ -14,8 +14,6 @@ using Pending = Context::Pending;
 // --- level-1 (reference: blasext, double/dblasext.F:6-255; dsafescal.F) ---------------------------
 // x <- a * x                                                     (pdscal dblasext.F:38)
 template <class T> void k_scal(Context& c, long n, T* x, real_t<T> a);
-// x <- x / (*slot).re, scalar taken from a device-resident result slot (speculative dsafescal)
-template <class T> void k_scal_inv_slot(Context& c, long n, T* x, const ScalarSlot* slot);
 // y <- y + a*x ; publish ||y||_2                                  (pdaxpy + pdnrm2 fused, dlanbpro.F:295-296)
 template <class T> void k_axpy_nrm(Context& c, long n, T a, const T* x, T* y, Pending* nrm);
 // publish conj(x).y                                              (pddot dblasext.F:121 / pzdotc)
@@ -27,7 +25,7 @@ template <class T> void k_zero(Context& c, long n, T* x);          // pdzero dbl
 // (bases_dev[r], peer memory) at offset rank*ld; arrival flags sit behind the world*ld elements of each buffer
 template <class T>
 void k_scal_push(Context& c, long n, long ld, T* x, real_t<T> a, void** bases_dev, int rank, int world, unsigned long long epoch,
-                 bool staggered, T* self_slice);
+                 T* self_slice);
 void k_wait_flags(Context& c, const unsigned long long* flags, unsigned int src_mask, unsigned long long epoch);
 // x(i) <- LAPACK xLARNV(idist=2, iseed) stream element offset+i, i=0..n-1 ; publish ||x||  (dgetu0.F:69-70).
 // `offset` = global index of this rank's first element in a row-sharded run (0 on one GPU).
@@ -54,21 +52,63 @@ template <class T> struct CsrDevice {
   const int* ci = nullptr;     // [nnz], sorted within a row
   const T* va = nullptr;       // [nnz]
   int lpr_log2 = 0;            // lanes per row in the reduce phase = 1 << lpr_log2 (csr_lanes_per_row_log2)
-  const int* long_rows = nullptr;  // rows with more than spmv_group_nnz/2 non-zeros (csr_long_rows), ascending
+  const int* long_rows = nullptr;  // rows done by spmv_long_kernel (k_csr_long_rows), ascending
   int n_long = 0;
 };
 // host-side analysis: lanes per row so that a group of 32/LPR rows fits a slice of nb products
 int csr_lanes_per_row_log2(long nnz, int rows, int nb);
-std::vector<int> csr_long_rows(const int* rp, int rows, int nb);
 // y <- op(A) x + coef*prev (prev may be null) ; optionally publish ||y||_2.  conj: use conj(values).
 template <class T>
 void k_spmv(Context& c, const CsrDevice<T>& A, bool conj, const T* x, T* y, real_t<T> coef, const T* prev, Pending* nrm);
+
+// The rows listed in A.long_rows, one CTA per row: y[row] = sum [+ y[row]] [+ coef*prev[row]] (spmv.cu).
+template <class T>
+void k_spmv_long(Context& c, const CsrDevice<T>& A, bool conj, const T* x, T* y, real_t<T> coef, const T* prev, bool accumulate);
+
+// --- sliced-ELL (SELL-32-sigma) SpMV, the default sparse APROD kernel (sell.cu) -----------------------------------
+constexpr int kSellSigma = 1024;     // rows per sorting window (rows are sorted by length inside a window)
+constexpr int kSellLong = 64;        // rows longer than this go to spmv_long_kernel (one CTA per row)
+constexpr int kSellCtasPerSm = 5;    // persistent CTAs per SM (no shared memory: L1 keeps the whole 228 KB)
+template <class T> struct SellDevice {
+  int rows = 0, cols = 0;
+  long nnz = 0;
+  long nslices = 0;                // 32-row slices (a multiple of kSellSigma/32; trailing slots carry perm = -1)
+  long long padded = 0;            // stored entries incl. padding
+  const long long* soff = nullptr; // [nslices+1] first entry of each slice (multiples of 32)
+  const int* perm = nullptr;       // [nslices*32] original row of a slot | 0x40000000 if the row is "long"; -1 = no row
+  const int* ci = nullptr;         // [padded] column, -1 = padding
+  const T* va = nullptr;           // [padded]
+};
+template <class T> struct SellStorage {
+  DeviceBuffer<long long> soff;
+  DeviceBuffer<int> perm, ci;
+  DeviceBuffer<T> va;
+  SellDevice<T> dev;
+};
+// CSR (device pointers, 0-based, sorted rows) -> SELL-32-sigma.  Integer work, deterministic.
+template <class T>
+void sell_build(Context& c, int rows, int cols, long nnz, const int* rp, const int* ci, const T* va, SellStorage<T>& out);
+// y <- [y +] op(S) x [+ coef*prev ; publish ||y||].  mode: bit 0 = accumulate into y, bit 1 = final phase (epilogue).
+// long_src: the CSR whose long_rows list spmv_long_kernel serves (final phase only), or null.
+// flags/src_mask/epoch: row-sharded runs -- wait in-kernel until the gather-buffer slices of the ranks in src_mask
+// have arrived (flags[r] >= epoch); src_mask = 0: no wait.
+constexpr int kSellModeAcc = 1, kSellModeFinal = 2;
+template <class T>
+void k_spmv_sell(Context& c, const SellDevice<T>& S, const CsrDevice<T>* long_src, bool conj, const T* x, T* y, real_t<T> coef,
+                 const T* prev, Pending* nrm, int mode, const unsigned long long* flags, unsigned int src_mask,
+                 unsigned long long epoch);
 
 // --- operator registration (setup): device-side transpose + validation, csr_build.cu ---------------------------
 // CSR(A) -> canonical CSR(A^T) (all device pointers).  Returns 0 / 1 (unsorted row) / 2 (index out of range).
 template <class T>
 int k_csr_transpose(Context& c, int rows, int cols, long nnz, const int* rp, const int* ci, const T* va, int* trp, int* tci, T* tva);
 void k_rebase(Context& c, long n, int* a, int base);  // a[i] -= base (Fortran 1-based index arrays)
+int k_csr_check_rowptr(Context& c, int rows, long nnz, const int* rp);   // 0, or 4 when rp is not monotone from 0 to nnz
+int k_csr_long_rows(Context& c, int rows, const int* rp, int threshold, DeviceBuffer<int>& list);  // rows longer than threshold
+// row-sharded operands: CSR -> G CSRs by the ring distance of each column's owner rank (csr_build.cu)
+template <class T>
+int k_csr_split_phases(Context& c, int rows, long width, const int* rp, const int* ci, const T* va, long ld, int P, int rank, int G,
+                       int* const* out_rp, DeviceBuffer<int>* const* out_ci, DeviceBuffer<T>* const* out_va, long* nnz_out);
 
 // synthetic dense operator A(i,j) = u(i,j) + planted rank-128 part, evaluated on the device (dense_gen.cu)
 void k_dense_synth(Context& c, long m, int n, long lda, unsigned long long seed, const double* table_host, double* A);

@@ -5,6 +5,7 @@
 // All are pure HBM streams; every vector access is a 128-bit pack, norms / dots are reduced in a
 // fixed order and published by the last CTA (common.cuh: grid_publish).
 #include <algorithm>
+#include <cstdlib>
 
 #include "kernels.cuh"
 
@@ -16,9 +17,8 @@ constexpr int L1_S = 2;  // packs per thread per iteration
 
 template <class T>
 __global__ void __launch_bounds__(kThreads)
-scal_kernel(long n, T* __restrict__ x, real_t<T> a, const ScalarSlot* slot) {
+scal_kernel(long n, T* __restrict__ x, real_t<T> a) {
   constexpr int VEC = Pack<T>::N;
-  if (slot != nullptr) a = real_t<T>(1) / real_t<T>(slot->re);
   const long np = (n + VEC - 1) / VEC;
   for (long i = (long)blockIdx.x * kThreads + threadIdx.x; i < np; i += (long)gridDim.x * kThreads) {
     Pack<T> p = ld_pack(x + i * VEC);
@@ -28,46 +28,32 @@ scal_kernel(long n, T* __restrict__ x, real_t<T> a, const ScalarSlot* slot) {
   }
 }
 
-// Fused "normalise + all-gather" of a row-sharded run: x <- a*x, and the scaled slice is also stored into every
-// rank's gather buffer (peer memory over NVLink; bases[r] = rank r's buffer) at this rank's offset.
-// STAGGERED = false: every pack goes to all destinations at once and the last CTA raises this rank's arrival flag
-// everywhere when everything is visible system-wide (fastest: one fence/ticket round).
-// STAGGERED = true (column-grouped SpMV experiment): destinations are served one after the other in ring order
-// (rank+1, rank+2, ...) and each destination's flag is raised as soon as ITS copy is complete.
-template <class T, bool STAGGERED>
+// Fused "normalise + all-gather" of a row-sharded run, in two kernels:
+//   scal_local_kernel (main stream)  x <- a*x, and a copy into this rank's own slice of its gather buffer;
+//   push_kernel (side stream, a few CTAs)  the scaled slice goes to every other rank's gather buffer over NVLink peer
+//   memory (bases[r] = rank r's buffer), one destination after the other in ring order (rank+1, rank+2, ...), and each
+//   destination's arrival flag is raised as soon as ITS copy is complete system-wide -- so slices land at a consumer in
+//   the order rank-1, rank-2, ... and its phase-split SpMV (sell.cu) starts on the early ones while the rest is in flight.
+// The push is NVLink-bound, not SM-bound: a thin grid leaves the SMs to the SpMV that runs concurrently.
+template <class T>
 __global__ void __launch_bounds__(kThreads)
-scal_push_kernel(long n, long ld, T* __restrict__ x, real_t<T> a, void** bases, int rank, int world, unsigned int* tickets,
-                 unsigned long long epoch) {
+push_kernel(long n, long ld, const T* __restrict__ x, void** bases, int rank, int world, unsigned int* tickets,
+            unsigned long long epoch) {
   constexpr int VEC = Pack<T>::N;
+  constexpr int PU = 4;   // packs in flight per thread
   __shared__ bool is_last;
   const long np = (n + VEC - 1) / VEC;
-  if (!STAGGERED) {
-    for (long i = (long)blockIdx.x * kThreads + threadIdx.x; i < np; i += (long)gridDim.x * kThreads) {
-      Pack<T> p = ld_pack(x + i * VEC);
-#pragma unroll
-      for (int e = 0; e < VEC; ++e) p.v[e] = a * p.v[e];  // padding stays 0
-      st_pack(x + i * VEC, p);
-      for (int r = 0; r < world; ++r) st_pack(static_cast<T*>(bases[r]) + (long)rank * ld + i * VEC, p);
-    }
-    __threadfence_system();
-    __syncthreads();
-    if (threadIdx.x == 0) is_last = (atomicAdd(tickets, 1u) == gridDim.x - 1);
-    __syncthreads();
-    if (is_last && threadIdx.x < world) {
-      unsigned long long* flags = reinterpret_cast<unsigned long long*>(static_cast<T*>(bases[threadIdx.x]) + (long)world * ld);
-      *reinterpret_cast<volatile unsigned long long*>(flags + rank) = epoch;
-      if (threadIdx.x == 0) tickets[0] = 0u;
-    }
-    return;
-  }
-  // (the scaling and the local copy were done on the main stream by scal_local_kernel; this kernel runs on the side
-  // stream and only moves the slice to the peers, so it overlaps the sub-SpMVs that consume the slices)
+  const long stride = (long)gridDim.x * kThreads;
   for (int d = 1; d < world; ++d) {
     const int dest = (rank + d) % world;
     T* dst = static_cast<T*>(bases[dest]) + (long)rank * ld;
-    // every thread re-reads exactly the packs it wrote above (program order makes them visible)
-    for (long i = (long)blockIdx.x * kThreads + threadIdx.x; i < np; i += (long)gridDim.x * kThreads)
-      st_pack(dst + i * VEC, ld_pack(x + i * VEC));
+    for (long i0 = (long)blockIdx.x * kThreads + threadIdx.x; i0 < np; i0 += stride * PU) {
+      Pack<T> p[PU];
+#pragma unroll
+      for (int u = 0; u < PU; ++u) if (i0 + u * stride < np) p[u] = ld_pack(x + (i0 + u * stride) * VEC);
+#pragma unroll
+      for (int u = 0; u < PU; ++u) if (i0 + u * stride < np) st_pack(dst + (i0 + u * stride) * VEC, p[u]);
+    }
     __threadfence_system();
     __syncthreads();
     if (threadIdx.x == 0) is_last = (atomicAdd(tickets + d, 1u) == gridDim.x - 1);
@@ -80,7 +66,7 @@ scal_push_kernel(long n, long ld, T* __restrict__ x, real_t<T> a, void** bases, 
   }
 }
 
-// x <- a*x and a copy into this rank's own slice of its gather buffer (main-stream half of the staggered push)
+// x <- a*x and a copy into this rank's own slice of its gather buffer (main-stream half of the push)
 template <class T>
 __global__ void __launch_bounds__(kThreads)
 scal_local_kernel(long n, T* __restrict__ x, real_t<T> a, T* __restrict__ self) {
@@ -97,11 +83,11 @@ scal_local_kernel(long n, T* __restrict__ x, real_t<T> a, T* __restrict__ self) 
 
 // Consumer side of the fused all-gather: returns once the slices of the ranks in `src_mask` (epoch `epoch`) have landed.
 __global__ void wait_flags_kernel(const unsigned long long* flags, unsigned int src_mask, unsigned long long epoch,
-                                  volatile unsigned int* host_err) {
+                                  volatile unsigned int* host_err, long long timeout_cycles) {
   if (!((src_mask >> threadIdx.x) & 1u)) return;
   const long long t0 = clock64();
   while (*reinterpret_cast<const volatile unsigned long long*>(flags + threadIdx.x) < epoch) {
-    if (clock64() - t0 > 20000000000LL) { *host_err = 1u; break; }   // ~10 s: a peer died; do not hang the GPU
+    if (clock64() - t0 > timeout_cycles) { *host_err = 1u; break; }   // a peer died; do not hang the GPU
   }
 }
 
@@ -231,34 +217,33 @@ template <class T> int l1_grid(Context& c, long n) {  // >= 1 CTA even for n = 0
 
 template <class T> void k_scal(Context& c, long n, T* x, real_t<T> a) {
   if (n <= 0) return;
-  scal_kernel<T><<<l1_grid<T>(c, n), kThreads, 0, c.stream>>>(n, x, a, nullptr);
+  scal_kernel<T><<<l1_grid<T>(c, n), kThreads, 0, c.stream>>>(n, x, a);
   PB_LAUNCH_CHECK();
   c.ctr.launches += 1;
 }
-template <class T> void k_scal_inv_slot(Context& c, long n, T* x, const ScalarSlot* slot) {
-  if (n <= 0) return;
-  scal_kernel<T><<<l1_grid<T>(c, n), kThreads, 0, c.stream>>>(n, x, real_t<T>(1), slot);
-  PB_LAUNCH_CHECK();
-  c.ctr.launches += 1;
+inline int push_ctas() {
+  static const int n = [] { const char* e = std::getenv("PROPACK_B200_PUSH_CTAS"); int v = e ? std::atoi(e) : 32; return std::min(148, std::max(1, v)); }();
+  return n;
 }
 template <class T>
 void k_scal_push(Context& c, long n, long ld, T* x, real_t<T> a, void** bases_dev, int rank, int world, unsigned long long epoch,
-                 bool staggered, T* self_slice) {
-  if (staggered) {
+                 T* self_slice) {
+  if (n > 0) {
     scal_local_kernel<T><<<l1_grid<T>(c, n), kThreads, 0, c.stream>>>(n, x, a, self_slice);
     PB_LAUNCH_CHECK();
-    PB_CUDA(cudaEventRecord(c.ev_fork, c.stream));
-    PB_CUDA(cudaStreamWaitEvent(c.stream2, c.ev_fork, 0));
-    scal_push_kernel<T, true><<<l1_grid<T>(c, n), kThreads, 0, c.stream2>>>(n, ld, x, a, bases_dev, rank, world, c.tickets8, epoch);
     c.ctr.launches += 1;
-  } else
-    scal_push_kernel<T, false><<<l1_grid<T>(c, n), kThreads, 0, c.stream>>>(n, ld, x, a, bases_dev, rank, world, c.tickets8, epoch);
+  }
+  // (a rank that owns no rows still raises its flags: the consumers wait for every source)
+  PB_CUDA(cudaEventRecord(c.ev_fork, c.stream));
+  PB_CUDA(cudaStreamWaitEvent(c.stream2, c.ev_fork, 0));
+  const int grid = (int)std::min<long>(push_ctas(), std::max<long>(1, ((n + Pack<T>::N - 1) / Pack<T>::N + kThreads - 1) / kThreads));
+  push_kernel<T><<<grid, kThreads, 0, c.stream2>>>(n, ld, x, bases_dev, rank, world, c.tickets8, epoch);
   PB_LAUNCH_CHECK();
   c.ctr.launches += 1;
 }
 void k_wait_flags(Context& c, const unsigned long long* flags, unsigned int src_mask, unsigned long long epoch) {
   if (src_mask == 0u) return;
-  wait_flags_kernel<<<1, 32, 0, c.stream>>>(flags, src_mask, epoch, c.host_err_dev);
+  wait_flags_kernel<<<1, 32, 0, c.stream>>>(flags, src_mask, epoch, c.host_err_dev, c.peer_timeout_cycles);
   PB_LAUNCH_CHECK();
   c.ctr.launches += 1;
 }
@@ -301,9 +286,8 @@ template <class T> void k_larnv_nrm(Context& c, long n, T* x, const int iseed[4]
 
 #define PB_INST(T)                                                                \
   template void k_scal<T>(Context&, long, T*, real_t<T>);                         \
-  template void k_scal_inv_slot<T>(Context&, long, T*, const ScalarSlot*);        \
   template void k_zero<T>(Context&, long, T*);                                    \
-  template void k_scal_push<T>(Context&, long, long, T*, real_t<T>, void**, int, int, unsigned long long, bool, T*); \
+  template void k_scal_push<T>(Context&, long, long, T*, real_t<T>, void**, int, int, unsigned long long, T*); \
   template void k_axpy_nrm<T>(Context&, long, T, const T*, T*, Pending*);         \
   template void k_dotc<T>(Context&, long, const T*, const T*, Pending*);          \
   template void k_nrm2<T>(Context&, long, const T*, Pending*);                    \

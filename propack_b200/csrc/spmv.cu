@@ -71,7 +71,7 @@ constexpr int kLongThreads = 128;
 // so the result is still deterministic (no atomics, fixed reduction order).
 template <class T, bool CONJ>
 __global__ void __launch_bounds__(kLongThreads)
-spmv_long_kernel(CsrDevice<T> A, const T* __restrict__ x, T* __restrict__ y, real_t<T> coef, const T* __restrict__ prev) {
+spmv_long_kernel(CsrDevice<T> A, const T* __restrict__ x, T* y, real_t<T> coef, const T* prev, int accumulate) {
   __shared__ T red[32];
   const int row = __ldg(A.long_rows + blockIdx.x);
   const int s = __ldg(A.rp + row), e = __ldg(A.rp + row + 1);
@@ -84,6 +84,7 @@ spmv_long_kernel(CsrDevice<T> A, const T* __restrict__ x, T* __restrict__ y, rea
   }
   acc = block_sum(acc, red);
   if (threadIdx.x == 0) {
+    if (accumulate) acc = acc + y[row];
     if (prev != nullptr) acc = acc + coef * prev[row];
     y[row] = acc;
   }
@@ -91,8 +92,7 @@ spmv_long_kernel(CsrDevice<T> A, const T* __restrict__ x, T* __restrict__ y, rea
 
 template <class T, bool CONJ>
 __global__ void __launch_bounds__(kThreads)
-spmv_kernel(CsrDevice<T> A, const T* __restrict__ x, T* __restrict__ y, real_t<T> coef, const T* __restrict__ prev,
-            ReduceWs ws, int want_norm) {
+spmv_kernel(CsrDevice<T> A, const T* __restrict__ x, T* y, real_t<T> coef, const T* prev, ReduceWs ws, int want_norm) {
   constexpr int NB = spmv_group_nnz<T>();
   constexpr int LONG = NB / 2;
   constexpr unsigned FULL = 0xffffffffu;
@@ -189,13 +189,7 @@ void k_spmv(Context& c, const CsrDevice<T>& A, bool conj, const T* x, T* y, real
     attr_set = true;
   }
   const bool cj = conj && scalar_traits<T>::is_complex;
-  c.set_l2_window(x, sizeof(T) * (size_t)A.cols);   // keep the gathered vector L2-resident while (ci, va) stream through
-  if (A.n_long > 0) {
-    if (cj) spmv_long_kernel<T, true><<<A.n_long, kLongThreads, 0, c.stream>>>(A, x, y, coef, prev);
-    else spmv_long_kernel<T, false><<<A.n_long, kLongThreads, 0, c.stream>>>(A, x, y, coef, prev);
-    PB_LAUNCH_CHECK();
-    c.ctr.launches += 1;
-  }
+  k_spmv_long<T>(c, A, cj, x, y, coef, prev, false);
   if (cj) spmv_kernel<T, true><<<grid, kThreads, 0, c.stream>>>(A, x, y, coef, prev, ws, want);
   else spmv_kernel<T, false><<<grid, kThreads, 0, c.stream>>>(A, x, y, coef, prev, ws, want);
   PB_LAUNCH_CHECK();
@@ -203,12 +197,13 @@ void k_spmv(Context& c, const CsrDevice<T>& A, bool conj, const T* x, T* y, real
   if (nrm) c.complete_reduce(*nrm, 1);
 }
 
-// Rows with more than half a slice of non-zeros (handled by spmv_long_kernel), ascending.
-std::vector<int> csr_long_rows(const int* rp, int rows, int nb) {
-  std::vector<int> out;
-  for (int i = 0; i < rows; ++i)
-    if (rp[i + 1] - rp[i] > nb / 2) out.push_back(i);
-  return out;
+template <class T>
+void k_spmv_long(Context& c, const CsrDevice<T>& A, bool cj, const T* x, T* y, real_t<T> coef, const T* prev, bool accumulate) {
+  if (A.n_long <= 0) return;
+  if (cj) spmv_long_kernel<T, true><<<A.n_long, kLongThreads, 0, c.stream>>>(A, x, y, coef, prev, accumulate ? 1 : 0);
+  else spmv_long_kernel<T, false><<<A.n_long, kLongThreads, 0, c.stream>>>(A, x, y, coef, prev, accumulate ? 1 : 0);
+  PB_LAUNCH_CHECK();
+  c.ctr.launches += 1;
 }
 
 // Lanes per row for a matrix with `nnz` non-zeros in `rows` rows: the largest row group (32/LPR rows) whose
@@ -223,7 +218,8 @@ int csr_lanes_per_row_log2(long nnz, int rows, int nb) {
 }
 
 #define PB_INST(T) \
-  template void k_spmv<T>(Context&, const CsrDevice<T>&, bool, const T*, T*, real_t<T>, const T*, Pending*);
+  template void k_spmv<T>(Context&, const CsrDevice<T>&, bool, const T*, T*, real_t<T>, const T*, Pending*); \
+  template void k_spmv_long<T>(Context&, const CsrDevice<T>&, bool, const T*, T*, real_t<T>, const T*, bool);
 PB_INST(float)
 PB_INST(double)
 PB_INST(cplx<float>)

@@ -281,3 +281,134 @@ def lanbpro(op: Operator, k0, k, U, V, B, rnorm, delta=None, eta=None, anorm=0.0
     if ierr.value <= -99:
         check(ierr.value, f"{pfx}lanbpro_")
     return kk.value, rn.value, ierr.value, float(doption[2])
+
+
+def ritzvec(which, U, V, D, E, k, jobu=True, jobv=True):
+    """xRITZVEC (reference double/dritzvec.F:1-2; complex zritzvec.F:1-2).  U (m, dim+1), V (n, dim) hold the Lanczos bases.
+    Returns (U[:, :k], V[:, :k], D_out) with D_out = singular values of the bidiagonal (descending)."""
+    U = np.array(U, order="F", copy=True)
+    V = np.array(V, order="F", copy=True)
+    pfx = PREFIX[U.dtype]
+    R = REAL[pfx]
+    D = np.array(D, dtype=R, copy=True)
+    E = np.array(E, dtype=R, copy=True)
+    S = np.zeros(max(k, 1), dtype=R)
+    dim = D.size
+    m, n = U.shape[0], V.shape[0]
+    work = np.zeros(8, dtype=R)
+    iwork = np.zeros(8, dtype=np.int32)
+    args = [which[:1].encode(), b"y" if jobu else b"n", b"y" if jobv else b"n", _i(m), _i(n), _i(k), _i(dim), _p(D), _p(E), _p(S),
+            _p(U), _i(m), _p(V), _i(n), _p(work), _i(work.size)]
+    if pfx in "cz":
+        zwork = np.zeros(8, dtype=U.dtype)
+        args += [_p(zwork), _i(zwork.size)]
+    args += [_p(iwork), C.c_size_t(1), C.c_size_t(1), C.c_size_t(1)]
+    getattr(lib(), f"{pfx}ritzvec_")(*args)
+    return U[:, :k], V[:, :k], D
+
+
+def gemm_ovwr(transa, A, B, m, n, k, alpha=1.0, beta=0.0):
+    """xGEMM_OVWR (reference double/dgemm_ovwr.F:5-6): returns alpha*op(A)*B + beta*B, written over B (m x n)."""
+    B = np.array(B, order="F", copy=True)
+    pfx = PREFIX[B.dtype]
+    A = np.asfortranarray(A, dtype=B.dtype)
+    work = np.zeros(max(m, 1), dtype=B.dtype)
+    getattr(lib(), f"{pfx}gemm_ovwr_")(transa.encode(), _i(m), _i(n), _i(k), _r(pfx, alpha), _p(A), _i(A.shape[0]), _r(pfx, beta),
+                                       _p(B), _i(B.shape[0]), _p(work), _i(work.size), C.c_size_t(1))
+    return B[:m, :n]
+
+
+_NRM2 = {"s": "psnrm2_", "d": "pdnrm2_", "c": "pscnrm2_", "z": "pdznrm2_"}
+_DOT = {"s": "psdot_", "d": "pddot_", "c": "pcdotc_", "z": "pzdotc_"}
+_AXPY = {"s": "psaxpy_", "d": "pdaxpy_", "c": "pcaxpy_", "z": "pzaxpy_"}
+_SCAL = {"s": "psscal_", "d": "pdscal_", "c": "pcsscal_", "z": "pzdscal_"}
+_ZERO = {"s": "pszero_", "d": "pdzero_", "c": "pczero_", "z": "pzzero_"}
+
+
+class _C8(C.Structure):
+    _fields_ = [("re", C.c_float), ("im", C.c_float)]
+
+
+class _C16(C.Structure):
+    _fields_ = [("re", C.c_double), ("im", C.c_double)]
+
+
+def _strided(x, inc):
+    """A buffer holding x at stride |inc| (BLAS layout for the given increment)."""
+    x = np.ascontiguousarray(x)
+    if inc == 1:
+        return x.copy()
+    buf = np.zeros(1 + (x.size - 1) * abs(inc) if x.size else 1, dtype=x.dtype)
+    if inc > 0:
+        buf[::inc][:x.size] = x
+    else:
+        buf[::-inc][:x.size] = x[::-1]
+    return buf
+
+
+def _unstrided(buf, n, inc):
+    if inc == 1:
+        return buf[:n].copy()
+    v = buf[::abs(inc)][:n]
+    return v.copy() if inc > 0 else v[::-1].copy()
+
+
+def nrm2(x, incx=1):
+    """pdnrm2 / psnrm2 / pdznrm2 / pscnrm2 (reference double/dblasext.F:6, complex16/zblasext.F:6)."""
+    x = np.ascontiguousarray(x)
+    pfx = PREFIX[x.dtype]
+    f = getattr(lib(), _NRM2[pfx])
+    f.restype = C.c_float if REAL[pfx] is np.float32 else C.c_double
+    return float(f(_i(x.size), _p(_strided(x, incx)), _i(incx)))
+
+
+def dotc(x, y, incx=1, incy=1):
+    """pddot / psdot / pzdotc / pcdotc (reference double/dblasext.F:121, complex16/zblasext.F:167): conj(x).y"""
+    x = np.ascontiguousarray(x)
+    y = np.ascontiguousarray(y, dtype=x.dtype)
+    pfx = PREFIX[x.dtype]
+    f = getattr(lib(), _DOT[pfx])
+    f.restype = {"s": C.c_float, "d": C.c_double, "c": _C8, "z": _C16}[pfx]
+    r = f(_i(x.size), _p(_strided(x, incx)), _i(incx), _p(_strided(y, incy)), _i(incy))
+    return complex(r.re, r.im) if pfx in "cz" else float(r)
+
+
+def axpy(alpha, x, y, incx=1, incy=1):
+    """pdaxpy / psaxpy / pzaxpy / pcaxpy (reference double/dblasext.F:92, complex16/zblasext.F:113): alpha*x + y"""
+    x = np.ascontiguousarray(x)
+    pfx = PREFIX[x.dtype]
+    yb = _strided(np.ascontiguousarray(y, dtype=x.dtype), incy)
+    a = np.array([alpha], dtype=x.dtype)
+    getattr(lib(), _AXPY[pfx])(_i(x.size), _p(a), _p(_strided(x, incx)), _i(incx), _p(yb), _i(incy))
+    return _unstrided(yb, x.size, incy)
+
+
+def scal(alpha, x, incx=1):
+    """pdscal / psscal / pzdscal / pcsscal (reference double/dblasext.F:38, complex16/zblasext.F:60): real alpha * x"""
+    x = np.ascontiguousarray(x)
+    pfx = PREFIX[x.dtype]
+    xb = _strided(x, incx)
+    getattr(lib(), _SCAL[pfx])(_i(x.size), _r(pfx, alpha), _p(xb), _i(incx))
+    return _unstrided(xb, x.size, incx)
+
+
+def zero(x, incx=1):
+    """pdzero / pszero / pzzero / pczero (reference double/dblasext.F:202, complex16/zblasext.F:344)"""
+    x = np.ascontiguousarray(x)
+    pfx = PREFIX[x.dtype]
+    xb = _strided(x, incx)
+    getattr(lib(), _ZERO[pfx])(_i(x.size), _p(xb), _i(incx))
+    return xb
+
+
+def sell_arrays(op: Operator, adjoint=False):
+    """The SELL-32-sigma copy of a registered CSR operator: dict(soff, perm, ci, va, sigma, long)."""
+    info = (C.c_longlong * 4)()
+    check(lib().propack_b200_csr_sell_info(C.c_int(op.handle), C.c_int(int(adjoint)), info), "csr_sell_info")
+    ns, padded = int(info[0]), int(info[1])
+    soff = np.zeros(ns + 1, dtype=np.int64)
+    perm = np.zeros(ns * 32, dtype=np.int32)
+    ci = np.zeros(max(padded, 1), dtype=np.int32)
+    va = np.zeros(max(padded, 1), dtype=op.dtype)
+    check(lib().propack_b200_csr_get_sell(C.c_int(op.handle), C.c_int(int(adjoint)), _p(soff), _p(perm), _p(ci), _p(va)), "csr_get_sell")
+    return dict(soff=soff, perm=perm, ci=ci[:padded], va=va[:padded], sigma=int(info[2]), long=int(info[3]))

@@ -2,8 +2,9 @@
 """Multi-GPU parity check, one process per GPU:  torchrun --nproc-per-node N tests/dist_check.py
 
 Runs the row-sharded DLANSVD / ZLANSVD / DLANSVD_IRL on N GPUs and checks, on rank 0, against dense LAPACK SVD and
-the CPU oracle (test infrastructure): sigma to 1e-10 relative, residuals, orthogonality -- the same bars as the
-single-GPU driver tests.  Prints DIST_CHECK_OK on success.
+the CPU oracle (test infrastructure): sigma to 1e-10 relative, residuals, orthogonality, and the same number of Lanczos
+steps and restarts as the oracle -- the same bars as the single-GPU driver tests.  The last case is the BASELINE
+configs[4] shape at DIST_CHECK_LARGE_ROWS rows (default 1M; 0 skips it).  Prints DIST_CHECK_OK on success.
 """
 import os
 import sys
@@ -34,7 +35,7 @@ def rand_sparse(rng, m, n, density, dtype):
     return A
 
 
-def run_case(name, A, k, kmax, rank, world, irl=None, tol=1e-12):
+def run_case(name, A, k, kmax, rank, world, irl=None, tol=1e-12, dense_check=True, maxiter=200):
     m, n = A.shape
     dtype = A.dtype
     u0 = np.random.default_rng(1).uniform(size=m).astype(dtype)
@@ -42,35 +43,53 @@ def run_case(name, A, k, kmax, rank, world, irl=None, tol=1e-12):
     lanmax = min(m + 1, n + 1, kmax)
     sv = pdist.Solver(op, lanmax + 1, lanmax)
     sv.set_start(u0)
+    propack_b200.reset_counters()
     if irl is None:
         r = sv.lansvd(k, kmax, tol=tol, cgs=True)
     else:
-        r = sv.lansvd_irl("L", irl[0], irl[1], k, 200, tol=tol, cgs=True)
+        r = sv.lansvd_irl("L", irl[0], irl[1], k, maxiter, tol=tol, cgs=True)
+    ctr = propack_b200.counters()
     U = pdist.gather_rows(r["U"], m)
     V = pdist.gather_rows(r["V"], n)
     ok = True
     if rank == 0:
         S = r["sigma"]
-        sd = np.linalg.svd(A.toarray(), compute_uv=False)[:k]
         eps = np.finfo(dtype).eps
-        e_sig = relerr(S, sd)
+        e_sig = relerr(S, np.linalg.svd(A.toarray(), compute_uv=False)[:k]) if dense_check else float("nan")
         res = float(np.max(np.linalg.norm(A @ V - U * S, axis=0)))
         orth = float(max(np.max(np.abs(U.conj().T @ U - np.eye(k))), np.max(np.abs(V.conj().T @ V - np.eye(k)))))
         # the CPU oracle on the same inputs (same start vector): parity of the algorithm, not only of the answer
         from oracle import oracle_py as O
+        O.stats_reset()
         if irl is None:
-            ref = O.lansvd(A, k, kmax, tol=tol, u0=u0, cgs=True, dtype=dtype)
+            ref = O.lansvd(A, k, kmax, tol=tol, u0=u0, cgs=True, dtype=dtype, jobu=False, jobv=False)
         else:
-            ref = O.lansvd_irl(A, k, irl[0], p=irl[1], which="L", maxiter=200, tol=tol, u0=u0, cgs=True, dtype=dtype)
+            ref = O.lansvd_irl(A, k, irl[0], p=irl[1], which="L", maxiter=maxiter, tol=tol, u0=u0, cgs=True, dtype=dtype,
+                               jobu=False, jobv=False)
+        st = O.stats()
         e_ref = relerr(S, ref["sigma"][:k]) if ref["k"] >= k else float("nan")
-        ok = (r["info"] == 0 and r["k"] == k and e_sig < 1e-10 and res < 1e-8 * S[0] and orth < 200 * np.sqrt(eps)
-              and (np.isnan(e_ref) or e_ref < 1e-10))
+        same_path = ctr["nsteps"] == st["nsteps"] and ctr["nrestart"] == st["nrestart"]
+        ok = (r["info"] == 0 and r["k"] == k and (np.isnan(e_sig) or e_sig < 1e-10) and res < 1e-8 * S[0]
+              and orth < 200 * np.sqrt(eps) and ref["k"] >= k and e_ref < 1e-10 and same_path)
         print(f"[dist_check] {name}: world={world} info={r['info']} k={r['k']} sigma_relerr_dense={e_sig:.2e} "
-              f"sigma_relerr_oracle={e_ref:.2e} max_residual={res:.2e} orth={orth:.2e} -> {'ok' if ok else 'FAIL'}", flush=True)
+              f"sigma_relerr_oracle={e_ref:.2e} max_residual={res:.2e} orth={orth:.2e} steps={ctr['nsteps']}/{st['nsteps']} "
+              f"restarts={ctr['nrestart']}/{st['nrestart']} -> {'ok' if ok else 'FAIL'}", flush=True)
     sv.close(); op.close()
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.broadcast(flag, src=0)
     return bool(flag.item())
+
+
+def c5_pattern(m, n, per=10):
+    """BASELINE configs[4] pattern: exactly `per` uniform columns per row (bench.make_matrix 'c5')."""
+    rng = np.random.default_rng(0)
+    cols = rng.integers(0, n, size=(m, per), dtype=np.int32)
+    cols.sort(axis=1)
+    vals = rng.standard_normal(size=(m, per))
+    A = sp.csr_array((vals.ravel(), cols.ravel(), np.arange(0, m * per + 1, per, dtype=np.int64)), shape=(m, n))
+    A.sum_duplicates()
+    A.sort_indices()
+    return A
 
 
 def main():
@@ -85,8 +104,12 @@ def main():
     ok &= run_case("d 4000x40 lansvd (ranks without columns)", rand_sparse(rng, 4000, 40, 0.2, np.float64), 5, 41, rank, world)
     ok &= run_case("z 1500x1200 zlansvd", rand_sparse(rng, 1500, 1200, 0.01, np.complex128), 6, 150, rank, world)
     ok &= run_case("d 3000x2000 lansvd_irl", rand_sparse(rng, 3000, 2000, 0.005, np.float64), 6, 60, rank, world, irl=(40, 20), tol=1e-10)
+    # the config-5 shape of the north star (k=100, DLANSVD_IRL dim=300 p=200: restarts, the 101-column restart GEMM)
+    rows_large = int(os.environ.get("DIST_CHECK_LARGE_ROWS", "1000000"))
+    if rows_large > 0:
+        ok &= run_case(f"d {rows_large}x{rows_large} c5 pattern lansvd_irl dim=300 p=200", c5_pattern(rows_large, rows_large), 100, 300,
+                       rank, world, irl=(300, 200), tol=1e-10, dense_check=False, maxiter=50)
     if rank == 0:
-        print("comm stats:", propack_b200.counters()["launches"], flush=True)
         print("DIST_CHECK_OK" if ok else "DIST_CHECK_FAILED", flush=True)
     pdist.finalize_comm()
     dist.destroy_process_group()

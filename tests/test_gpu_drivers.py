@@ -228,6 +228,14 @@ def test_lanbpro_factorisation_and_extension(oracle, dtype):
     assert np.max(np.abs(U.conj().T @ U - np.eye(k + 1))) < 1e-7
     assert np.max(np.abs(V.conj().T @ V - np.eye(k))) < 1e-7
     assert abs(rnorm - B[k - 1, 1]) == 0
+    # the same bidiagonal as the oracle's dlanbpro on the same inputs (alpha = B(:,1), beta = B(:,2)), both legs
+    Uo = np.zeros_like(U); Vo = np.zeros_like(V); Bo = np.zeros_like(B)
+    Uo[:, 0] = u0
+    ko, rn_o, ierr_o, an_o = oracle.lanbpro(A, 0, 12, Uo, Vo, Bo, float(np.linalg.norm(u0)), dtype=dtype)
+    ko, rn_o, ierr_o, an_o = oracle.lanbpro(A, 12, k, Uo, Vo, Bo, rn_o, anorm=an_o, dtype=dtype)
+    assert ko == k
+    assert np.max(np.abs(B - Bo) / np.abs(Bo)) < 1e-10
+    assert abs(rn_o - rnorm) < 1e-10 * rnorm and abs(an_o - anorm) < 1e-10 * anorm
     op.close()
 
 

@@ -215,3 +215,144 @@ def test_safescal(oracle, dtype):
         y = f77.safescal(xs, tiny)
         want = xs.real / tiny + 1j * (xs.imag / tiny) if np.iscomplexobj(xs) else xs / tiny  # numpy's complex '/' overflows here
         assert rel(y, want) < 1e-12
+
+
+# ---------------------------------------------------------------------------------------------------------
+# SELL-32-sigma construction (integer work: bit-exact) and the SELL SpMV on awkward shapes
+# ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype", [np.float64, np.complex128])
+@pytest.mark.parametrize("shape", [(700, 3100), (2500, 900), (1024, 64)])
+def test_sell_build_is_bit_exact(dtype, shape):
+    """The device-built SELL copies of A and A^T equal the numpy restatement (tests/sell_ref.py) array for array."""
+    from propack_b200 import f77
+    from sell_ref import sell_ref
+    rng = np.random.default_rng(2)
+    A = ragged_matrix(rng, *shape, dtype)
+    op = f77.Operator(A)
+    At = sp.csr_array(A.T)
+    At.sort_indices()
+    for adjoint, M in ((False, A), (True, At)):
+        got = f77.sell_arrays(op, adjoint)
+        want = sell_ref(M, sigma=got["sigma"], long_thr=got["long"])
+        assert np.array_equal(got["soff"], want["soff"])
+        assert np.array_equal(got["perm"], want["perm"])
+        assert np.array_equal(got["ci"], want["ci"])
+        assert np.array_equal(got["va"], want["va"])
+    op.close()
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_aprod_uniform_rows_and_tiny_shapes(oracle, dtype):
+    """Exactly-10-per-row matrices (the config 5 pattern, no padding at all), a 1 x 1 matrix and a single column."""
+    from propack_b200 import f77
+    rng = np.random.default_rng(3)
+    m, n = 5000, 4100
+    cols = np.sort(rng.integers(0, n, size=(m, 10)), axis=1)
+    A = sp.csr_array((rand_vec(rng, m * 10, dtype), cols.ravel(), np.arange(0, m * 10 + 1, 10)), shape=(m, n))
+    A.sum_duplicates(); A.sort_indices()
+    cplx = np.iscomplexobj(np.zeros(1, dtype=dtype))
+    cases = [A, sp.csr_array(np.array([[3.0]], dtype=dtype)), sp.csr_array(rand_vec(rng, 77, dtype).reshape(77, 1))]
+    for M in cases:
+        op = f77.Operator(M)
+        for transa in ("n", "c" if cplx else "t"):
+            x = rand_vec(rng, M.shape[1] if transa == "n" else M.shape[0], dtype)
+            got = f77.aprod(op, transa, x)
+            want = oracle.csr_aprod(transa, M, x, dtype=dtype)
+            assert rel(got, want) < TOL[dtype] * 1e-2
+        op.close()
+
+
+def test_csr_create_rejects_malformed_input():
+    """Row pointers that decrease / overshoot, unsorted rows and out-of-range columns are refused (no device faults)."""
+    from propack_b200 import _lib
+    L = _lib.lib()
+    f = L.propack_b200_csr_create_d
+    va = np.ones(4)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    bad_rp = np.array([0, 3, 2, 4], dtype=np.int32); ci = np.array([0, 1, 2, 0], dtype=np.int32)
+    assert f(3, 3, p(bad_rp), p(ci), p(va), 0) < 0 and "non-decreasing" in _lib.last_error()
+    rp = np.array([0, 2, 3, 4], dtype=np.int32); unsorted = np.array([1, 0, 2, 0], dtype=np.int32)
+    assert f(3, 3, p(rp), p(unsorted), p(va), 0) < 0 and "sorted" in _lib.last_error()
+    oob = np.array([0, 3, 2, 0], dtype=np.int32)
+    assert f(3, 3, p(rp), p(oob), p(va), 0) < 0 and "out of range" in _lib.last_error()
+
+
+# ---------------------------------------------------------------------------------------------------------
+# blasext level-1 (pdnrm2 / pddot / pdaxpy / pdscal / pdzero and s/c/z variants), through the exported symbols
+# ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("n", [1, 31, 4097, 300_001])
+def test_blasext_level1_matches_oracle(oracle, dtype, n):
+    from propack_b200 import f77
+    rng = np.random.default_rng(n)
+    x, y = rand_vec(rng, n, dtype), rand_vec(rng, n, dtype)
+    tol = TOL[dtype] * 1e-2
+    assert abs(f77.nrm2(x) - oracle.nrm2(x)) <= tol * oracle.nrm2(x)
+    d_got, d_want = f77.dotc(x, y), oracle.dotc(x, y)
+    assert abs(d_got - d_want) <= tol * np.linalg.norm(x) * np.linalg.norm(y)
+    alpha = dtype(0.75) if not np.iscomplexobj(x) else dtype(0.75 - 0.5j)
+    assert rel(f77.axpy(alpha, x, y), oracle.axpy(alpha, x, y)) < tol
+    assert rel(f77.scal(-1.5, x), oracle.scal(-1.5, x)) < tol
+    assert not np.any(f77.zero(x))
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.complex128])
+def test_blasext_level1_increments(dtype):
+    """Non-unit and negative increments follow the BLAS convention (dblasext.F:154-196 forwards them to the BLAS)."""
+    from propack_b200 import f77
+    rng = np.random.default_rng(5)
+    n = 1000
+    x, y = rand_vec(rng, n, dtype), rand_vec(rng, n, dtype)
+    assert abs(f77.nrm2(x, incx=3) - np.linalg.norm(x)) < 1e-12 * np.linalg.norm(x)
+    assert abs(f77.dotc(x, y, incx=2, incy=-1) - np.vdot(x, y)) < 1e-10
+    assert rel(f77.axpy(2.0, x, y, incx=-2, incy=3), 2.0 * x + y) < 1e-13
+    assert rel(f77.scal(0.5, x, incx=2), 0.5 * x) < 1e-15
+
+
+# ---------------------------------------------------------------------------------------------------------
+# xRITZVEC and xGEMM_OVWR entry points
+# ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("which", ["L", "S"])
+def test_ritzvec_matches_oracle(oracle, dtype, which):
+    """dritzvec_ on a genuine Lanczos factorisation (bases and bidiagonal from dlanbpro_): the same Ritz vectors as the oracle's
+    dritzvec, and D returns the singular values of B."""
+    from propack_b200 import f77
+    rng = np.random.default_rng(11)
+    A = rand_sparse(rng, 1200, 700, 0.02, dtype)
+    op = f77.Operator(A)
+    m, n = A.shape
+    dim, k = 40, 6
+    R = np.float32 if dtype in (np.float32, np.complex64) else np.float64
+    U = np.zeros((m, dim + 1), dtype=dtype, order="F"); V = np.zeros((n, dim), dtype=dtype, order="F")
+    B = np.zeros((dim, 2), dtype=R, order="F")
+    u0 = rng.uniform(size=m).astype(dtype)
+    U[:, 0] = u0
+    kk, rnorm, ierr, _ = f77.lanbpro(op, 0, dim, U, V, B, float(np.linalg.norm(u0)), cgs=True)
+    assert kk == dim
+    gu, gv, gd = f77.ritzvec(which, U, V, B[:, 0], B[:, 1], k)
+    wu, wv, wd = oracle.ritzvec(which, U, V, B[:, 0], B[:, 1], k)
+    tol = TOL[dtype]
+    assert np.max(np.abs(gd - wd)) < tol * wd[0]
+    for i in range(k):
+        for g, w in ((gu, wu), (gv, wv)):
+            ph = np.vdot(w[:, i], g[:, i])
+            ph = ph / abs(ph)
+            assert np.linalg.norm(g[:, i] - ph * w[:, i]) < (1e-3 if R is np.float32 else 1e-8)
+    op.close()
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("transa", ["n", "t"])
+def test_gemm_ovwr_matches_definition(dtype, transa):
+    """dgemm_ovwr_: B <- alpha*op(A)*B + beta*B (dgemm_ovwr.F:5-53) for the (dim) x (dim+1) shapes dritzvec uses and a ragged one."""
+    from propack_b200 import f77
+    rng = np.random.default_rng(9)
+    for (m, n, k) in [(40, 41, 40), (17, 9, 23), (1, 1, 1)]:
+        A = rng.standard_normal((m, k) if transa == "n" else (k, m)).astype(dtype)
+        B = rng.standard_normal((max(m, k), n)).astype(dtype)
+        opA = A if transa == "n" else A.T
+        for alpha, beta in ((1.0, 0.0), (-0.5, 2.0)):
+            want = alpha * (opA.astype(np.float64) @ B[:k].astype(np.float64)) + beta * B[:m].astype(np.float64)
+            got = f77.gemm_ovwr(transa, A, B, m, n, k, alpha, beta)
+            assert rel(got, want) < TOL[dtype] * 1e-1
