@@ -1,22 +1,24 @@
 #!/usr/bin/env python
 """bench.py -- headline measurement of the PROPACK Lanczos-bidiagonalisation hot path on B200.
 
-    python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload c2|c2-small|c5-1gpu]
+    python bench.py --gpus N --steps K --warmup W [--impl reference|scipy] [--workload c5|c2|c3|c4|...]
 
-One "step" = one complete DLANSVD solve (time to k triplets) of the workload below; the metric is
-whole-job Lanczos steps per second (BASELINE.json metric "time to k triplets + Lanczos steps/s"),
-with the time to k triplets reported as ms_per_step.
+One "step" = one complete solve (time to k triplets) of the workload; the metric is whole-job Lanczos steps per second
+(BASELINE.json metric "time to k triplets + Lanczos steps/s"), with the time to k triplets reported as ms_per_step.
 
-Workload at N=1 (BASELINE.json configs[1], "C2"): synthetic random CSR 1M x 1M, ~10 nnz/row, N(0,1)
-values (scipy.sparse.random_array, default_rng(0)), k=50, kmax=600, tol=1e-10, DLANSVD double, CGS
-reorthogonalisation, start vector default_rng(1).uniform.  Inputs (120 MB matrix + 2 x 4.8 GB bases) are
-far larger than the 126 MB L2, so no explicit L2 flush is needed between steps.
+Default workload at every N (BASELINE.json configs[4], "C5", the north-star target): synthetic CSR 10M x 10M, exactly 10
+uniform columns per row (1e8 nnz), N(0,1) values, default_rng(0); top-100 triplets by DLANSVD_IRL (dim=300, p=200),
+tol=1e-10, double, CGS reorthogonalisation, start vector default_rng(1).uniform.  It fits one GPU (1.2 GB matrix x 2
+directions x 2 formats + 2 x 24 GB bases); N > 1 row-shards the same problem (strong scaling).  Inputs are far larger
+than the 126 MB L2, so no explicit L2 flush is needed between steps.  `--workload c2` is BASELINE configs[1].
 
-Keys (see the task contract): value / ms_per_step are device-timed (CUDA events on the library stream)
-with the matrix and start vector already resident in HBM; e2e goes through the Fortran-ABI `dlansvd_`
-with HOST buffers (matrix upload + start vector up, U/V/sigma back) inside the timed region; roofline is
-the reorthogonalisation GEMV pair, measured live with CUDA events in a profiled solve of the same workload;
-cpu_baseline is the CPU oracle (a port of the reference, OpenMP) on a bounded sample.
+Keys (see the task contract): value / ms_per_step are device-timed (CUDA events on the library stream) with the matrix
+and start vector already resident in HBM; e2e goes through the Fortran-ABI `dlansvd[_irl]_` with HOST buffers (matrix
+upload + start vector up, U/V/sigma back) inside the timed region; roofline describes the kernel with the largest share
+of the solve, measured live with CUDA events in a profiled solve of the same workload; cpu_baseline is the CPU oracle (a
+port of the reference, OpenMP) on a bounded sample.  `--impl reference` times the oracle's FULL solve of the same
+workload (same driver, k, tol, start vector: time to k triplets, like for like) on all host cores, plus SciPy's PROPACK
+translation (`scipy.sparse.linalg._svdp`) on a bounded 1/10-scale replica as an independent cross-check.
 """
 from __future__ import annotations
 
@@ -54,7 +56,11 @@ DENSE_SEED = 0
 DENSE_CPU_ROWS = {"c3": 100_000, "c3-small": 20_000}   # rows of the CPU arm's replica (cost per step is linear in rows)
 IRL_P = {"c5": 200, "c5-small": 200, "c3": 100, "c3-small": 50}   # workloads solved with DLANSVD_IRL: shifts per restart (kmax column = dim)
 IRL_MAXITER = 50
-CPU_SAMPLE_STEPS = 150  # Lanczos steps of the same problem the CPU baseline runs per sample
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel at working size, from the committed
+# `ncu --set full` captures (profiles/r02_ncu_extract.txt); filled in by hand from those files, None = not captured
+NCU_TRAFFIC_BYTES_PER_LAUNCH = {("c5", "spmv"): None, ("c5", "reorth"): None, ("c2", "spmv"): 140.03e6 + 5.3e6, ("c2", "reorth"): None}
+CPU_SAMPLE_STEPS = 150  # Lanczos steps of the same problem the in-line cpu_baseline runs (bounded sample, ~10-30 s)
+REF_BUDGET_S = 600.0    # --impl reference: stop adding full CPU solves once the projected run time passes this
 
 
 class DenseSpec:
@@ -212,6 +218,62 @@ def cpu_arm(name, A, u0, steps):
     return v, dt, cores, ""
 
 
+def cpu_full_solve(name, A, u0, k, kmax, tol):
+    """The oracle's complete driver run of the workload (time to k triplets incl. Ritz vectors) on all host cores.
+    Returns (seconds, steps, converged, info, cores, sigma, note)."""
+    from oracle import oracle_py as O
+    L = O.lib()
+    note = ""
+    if isinstance(A, DenseSpec):
+        rows = min(DENSE_CPU_ROWS[name], A.shape[0])
+        Am = A.replica(rows)
+        u0 = u0[:rows]
+        note = (f"dense replica with the first {rows} of {A.shape[0]} rows (the full matrix is 65.5 GB and is only ever generated on the "
+                f"device); steps/s scaled by {rows / A.shape[0]:.4f} because every per-step cost is linear in the row count")
+    else:
+        Am = A
+    O.stats_reset()
+    t0 = time.perf_counter()
+    if name in IRL_P:
+        r = O.lansvd_irl(Am, k, kmax, p=IRL_P[name], which="L", maxiter=IRL_MAXITER, tol=tol, u0=u0, cgs=True, dtype=np.dtype(Am.dtype))
+    else:
+        r = O.lansvd(Am, k, kmax, tol=tol, u0=u0, cgs=True, dtype=np.dtype(Am.dtype))
+    dt = time.perf_counter() - t0
+    scale = (Am.shape[0] / A.shape[0]) if isinstance(A, DenseSpec) else 1.0
+    return dt / scale, O.stats()["nsteps"], r["k"], r["info"], int(L.oracle_num_threads()), r["sigma"], note
+
+
+def scipy_svdp_sample(name, budget_rows=1_000_000):
+    """SciPy's own PROPACK translation (scipy.sparse.linalg._svdp, the importable build of the reference: SURVEY 8c/8d item 2)
+    on a 1/10-scale replica of the sparse workloads, same driver parameters.  Returns a dict for the JSON line, or None."""
+    small = {"c5": "c5-small", "c2": "c2-small", "c4": "c4-small"}.get(name, name if name.endswith("-small") or name.endswith("-tiny") else None)
+    if small is None or small in DENSE:
+        return None
+    try:
+        from scipy.sparse.linalg._svdp import _svdp
+    except Exception as e:   # scipy without the PROPACK extension
+        return {"unavailable": repr(e)}
+    A, u0, k, kmax, tol = make_matrix(small)
+    if A.shape[0] > budget_rows:
+        return None
+    AT = A.T.tocsr()
+    calls = [0]
+    import scipy.sparse.linalg as spla
+    lop = spla.LinearOperator(A.shape, matvec=lambda x: (calls.__setitem__(0, calls[0] + 1), A @ x)[1],
+                              rmatvec=lambda x: (calls.__setitem__(0, calls[0] + 1), AT.conj() @ x)[1], dtype=A.dtype)
+    irl = small in IRL_P
+    t0 = time.perf_counter()
+    try:
+        u, sg, vh, bnd = _svdp(lop, k, which="LM", irl_mode=irl, kmax=kmax, v0=u0, tol=tol, cgs=True, shifts=IRL_P.get(small),
+                               maxiter=IRL_MAXITER if irl else None, full_output=True, rng=np.random.default_rng(0))
+    except Exception as e:
+        return {"workload": small, "error": repr(e)[:200]}
+    dt = time.perf_counter() - t0
+    return {"workload": f"{small}: {A.shape[0]}x{A.shape[1]}, nnz={A.nnz}, k={k}, {'IRL dim=%d p=%d' % (kmax, IRL_P[small]) if irl else 'kmax=%d' % kmax}",
+            "time_to_k_triplets_s": dt, "matvecs": calls[0], "steps_per_s": calls[0] / 2.0 / dt, "sigma_1": float(sg.max()),
+            "impl": "scipy.sparse.linalg._svdp (SciPy's C translation of PROPACK; scipy.sparse matvec callbacks)"}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -219,24 +281,49 @@ def run_reference(args):
     # torchrun exports OMP_NUM_THREADS=1 to every rank; the CPU arm uses all the host cores it can (set before libgomp loads)
     os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
     A, u0, k, kmax, tol = make_matrix(args.workload)
-    vals, secs, cores = [], [], 1
-    note = ""
-    for i in range(args.warmup + args.steps):
-        v, dt, cores, note = cpu_arm(args.workload, A, u0, CPU_SAMPLE_STEPS)
-        if i >= args.warmup:
-            vals.append(v); secs.append(dt)
-    value = float(np.mean(vals))
-    sample = (f"oracle DLANBPRO (C++/OpenMP port of the reference; Fortran not buildable here), first {CPU_SAMPLE_STEPS} "
-              f"Lanczos steps of the {args.workload} problem incl. partial reorthogonalisation, OpenMP CSR/CSC APROD" + ("; " + note if note else ""))
+    # Each step is a FULL solve (time to k triplets).  The run is bounded: after the first solve, further warm-up / timed solves
+    # are only done while the projected total stays under REF_BUDGET_S -- on config 5 one solve is minutes of CPU time.
+    secs, steps_per_solve, runs = [], 0, 0
+    t_start = time.perf_counter()
+    want = args.warmup + args.steps
+    res = None
+    while runs < want:
+        res = cpu_full_solve(args.workload, A, u0, k, kmax, tol)
+        runs += 1
+        secs.append(res[0]); steps_per_solve = res[1]
+        elapsed = time.perf_counter() - t_start
+        if elapsed + res[0] > REF_BUDGET_S:
+            break
+    dt, nsteps, kc, info, cores, sigma, note = res
+    timed = secs[min(args.warmup, len(secs) - 1):]          # drop warm-up solves when there was time for them
+    mean_s = float(np.mean(timed))
+    value = steps_per_solve / mean_s
+    sample = (f"oracle {'DLANSVD_IRL' if args.workload in IRL_P else ('ZLANSVD' if args.workload in COMPLEX else 'DLANSVD')} (C++/OpenMP port of "
+              f"the reference; Fortran not buildable here), FULL solve of the {args.workload} problem to k={k} converged triplets incl. Ritz "
+              f"vectors ({nsteps} Lanczos steps, converged={kc}, info={info}), OpenMP CSR/CSC APROD; {len(secs)} solve(s) run, "
+              f"{len(timed)} timed (requested warmup={args.warmup} steps={args.steps}, bounded by {REF_BUDGET_S:.0f} s)" + ("; " + note if note else ""))
     line = {
         "impl": "reference", "metric": "lanczos_steps_per_s", "value": value, "unit": "steps/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * float(np.mean(secs)), "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": wl_dtype(args.workload)[0], "data": "synthetic",
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * mean_s, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": wl_dtype(args.workload)[0], "data": "synthetic",
         "config": config_dict(args.workload, A, k, kmax, tol),
+        "time_to_k_triplets_s": mean_s, "lanczos_steps_per_solve": int(steps_per_solve), "converged": int(kc), "info": int(info),
+        "sigma_1": float(sigma[0]) if kc else None, "sigma_k": float(sigma[kc - 1]) if kc else None,
         "cpu_baseline": {"value": value, "unit": "steps/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
+    if not args.no_scipy and time.perf_counter() - t_start < REF_BUDGET_S:
+        sc = scipy_svdp_sample(args.workload)
+        if sc:
+            line["scipy_svdp"] = sc
     print(json.dumps(line))
+
+
+def run_scipy(args):
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
+    print(json.dumps({"impl": "scipy", "scipy_svdp": scipy_svdp_sample(args.workload, budget_rows=10**9)}))
 
 
 def config_dict(name, A, k, kmax, tol):
@@ -356,8 +443,7 @@ def run_ours(args):
     # reorthogonalisation GEMV pair); both are HBM streams, timed with CUDA events on the library stream
     tot_ms = sum(v["ms"] for v in ph.values())
     aprod_ms = ph["aprod"]["ms"]
-    # ncu --set full, per launch, C2 operands (profiles/r01_ncu_full_extract.txt): dram read + write
-    traffic_known = {("c2", "spmv"): 140.03e6 + 5.3e6, ("c2", "reorth"): None}
+    traffic_known = NCU_TRAFFIC_BYTES_PER_LAUNCH
     if aprod_ms >= reorth_ms:
         kname = ("dense APROD = gemv_n_kernel / gemv_t_kernel + gemv_t_finalize over A itself" if isinstance(A, DenseSpec) else
                  "spmv_kernel (CSR gather SpMV, fused axpy + norm; + spmv_long_kernel on power-law rows)")
@@ -448,16 +534,16 @@ def run_ours(args):
         v, dt, cores, note = cpu_arm(args.workload, A, u0, CPU_SAMPLE_STEPS)
         cpu = {"value": v, "unit": "steps/s", "cores": cores, "kind": "port",
                "sample": f"oracle DLANBPRO (C++/OpenMP port; the Fortran reference cannot be compiled in this image), first "
-                         f"{CPU_SAMPLE_STEPS} Lanczos steps of the same problem ({dt:.1f} s); early steps reorthogonalise against "
-                         f"fewer columns than the run average, so this overstates the CPU rate" + ("; " + note if note else "")}
+                         f"{CPU_SAMPLE_STEPS} Lanczos steps of the same problem ({dt:.1f} s) -- a bounded sample: early steps reorthogonalise "
+                         f"against fewer columns than the run average, so this overstates the CPU rate; the like-for-like number is the full "
+                         f"CPU solve timed by `bench.py --impl reference`" + ("; " + note if note else "")}
     if rank == 0:
         ctr, sigma, kc, info = last
         line = {
             "metric": "lanczos_steps_per_s", "value": value, "unit": "steps/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": dts, "data": "synthetic",
-            "config": dict(config_dict(args.workload, A, k, kmax, tol),
-                           parallelism=("single GPU" if world == 1 else f"{world} independent replicas (row-sharded path not in this round)")),
+            "scaling": "strong", "vs_baseline": None, "dtype": dts, "data": "synthetic",
+            "config": config_dict(args.workload, A, k, kmax, tol), "parallelism": "single GPU",
             "time_to_k_triplets_s": total_ms / args.steps / 1e3, "lanczos_steps_per_solve": ctr["nsteps"],
             "converged": kc, "info": info, "sigma_1": float(sigma[0]) if kc else None, "sigma_k": float(sigma[-1]) if kc else None,
             "gpu_launches": int(launches), "host_syncs_per_solve": ctr["host_syncs"],
@@ -582,11 +668,11 @@ def run_ours_sharded(args):
             "metric": "lanczos_steps_per_s", "value": value, "unit": "steps/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": wl_dtype(args.workload)[0], "data": "synthetic",
-            "config": dict(config_dict(args.workload, A, k, kmax, tol),
-                           parallelism=f"rows of A and U, and V-vectors, block-sharded over {world} GPUs; all-gather of the SpMV input, "
-                                       f"all-reduce of reorthogonalisation coefficients and norm partials fused into the producing "
-                                       f"kernels over NVLink peer memory (NCCL for the un-staged products); collectives_total counts "
-                                       f"the NCCL calls that remain"),
+            "config": config_dict(args.workload, A, k, kmax, tol),
+            "parallelism": (f"rows of A and U, and V-vectors, block-sharded over {world} GPUs; the SpMV input is pushed slice by slice over "
+                            f"NVLink peer memory by a thin side-stream kernel while the phase-split SpMV consumes the slices that have "
+                            f"landed; all-reduce of reorthogonalisation coefficients and norm partials fused into the producing kernels "
+                            f"(NCCL for the un-staged products); collectives_total counts the NCCL calls that remain"),
             "time_to_k_triplets_s": total_ms / args.steps / 1e3, "lanczos_steps_per_solve": ctr["nsteps"], "converged": kc,
             "info": info, "sigma_1": float(sigma[0]) if kc else None, "sigma_k": float(sigma[-1]) if kc else None,
             "gpu_launches": int(launches), "host_syncs_per_solve": ctr["host_syncs"],
@@ -610,13 +696,16 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "scipy"])
+    ap.add_argument("--workload", default="c5", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-scipy", action="store_true", help="(reference arm) skip the bounded SciPy _svdp cross-check")
     ap.add_argument("--no-e2e", action="store_true", help="(sharded arm, experiments only) skip the end-to-end leg")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.impl == "scipy":
+        run_scipy(args)
     elif int(os.environ.get("WORLD_SIZE", "1")) > 1:
         run_ours_sharded(args)
     else:

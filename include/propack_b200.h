@@ -245,11 +245,13 @@ int propack_b200_csr_create_c(int m, int n, const int* rowptr, const int* colind
 int propack_b200_csr_create_z(int m, int n, const int* rowptr, const int* colind, const pb200_complex16* values, int index_base);
 /* Copy back the device-built transpose (CSR of A^T, 0-based, sorted) -- integer work is bit-exact and testable. */
 int propack_b200_csr_get_transpose(int handle, int* t_rowptr, int* t_colind, void* t_values);
-/* The SELL-32-sigma copy the default SpMV kernel streams (adjoint = 1: the copy of A^T): info4 = slices, stored entries
- * incl. padding, sigma (rows per sorting window), long-row threshold; then the arrays themselves (slice_offsets[slices+1],
- * perm[32*slices] = original row | 0x40000000 for a long row, -1 = no row; colind/values[stored], column -1 = padding). */
-int propack_b200_csr_sell_info(int handle, int adjoint, long long* info4);
-int propack_b200_csr_get_sell(int handle, int adjoint, long long* slice_offsets, int* perm, int* colind, void* values);
+/* The sliced jagged-ELL copy the default SpMV kernel streams (adjoint = 1: the copy of A^T; panel = column block, 0 for
+ * operators whose gathered vector fits L2): info4 = slices (32 rows each), stored entries, number of panels, long-row
+ * threshold; then the arrays (slice_offsets[slices+1]; row_len[rows], 0xFF = long row kept in CSR; colind/values[stored],
+ * inside a slice first the 0-th entries of its rows in row order, then the 1-st entries, ...). */
+int propack_b200_csr_sell_info(int handle, int adjoint, int panel, long long* info4);
+int propack_b200_csr_get_sell(int handle, int adjoint, int panel, long long* slice_offsets, unsigned char* row_len, int* colind,
+                              void* values);
 /* Dense column-major m x n operator; host array is copied (…_create) or a device array is adopted, not copied
  * (…_adopt_device; it must stay alive; base 16-byte aligned, lda in elements and a multiple of the 128-bit pack (2 doubles),
  * rows m..lda-1 of every column zero -- the GEMV kernels read whole packs). */
@@ -325,6 +327,7 @@ int propack_b200_init(void);                         /* create the context on th
 int propack_b200_set_stream(void* cuda_stream);      /* run on a caller stream (e.g. torch's current stream) */
 int propack_b200_set_lapack(const char* path);       /* shared object providing {d,s}bdsqr / {d,s}bdsdc */
 int propack_b200_set_option(const char* name, int value); /* "peer_timeout_s": give up on a silent peer rank after this many seconds (default 30) */
+void propack_b200_release_cache(void);               /* free the Krylov-basis buffers parked for reuse by the next driver call of the same shape */
 void propack_b200_set_profile(int on);               /* per-phase CUDA-event timers (adds synchronisation) */
 void propack_b200_reset_counters(void);
 /* out[0..15] = nopx nreorth ndot nitref nrestart nbsvd nlandim nsing nsteps reorth_passes reorth_cols

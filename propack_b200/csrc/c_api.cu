@@ -110,8 +110,11 @@ template <class T> int csr_create(int m, int n, const int* rowptr, const int* co
   const int st = k_csr_transpose<T>(c, m, n, nnz, op->rp.p, op->ci.p, op->va.p, op->trp.p, op->tci.p, op->tva.p);
   if (st & 2) throw std::runtime_error("propack_b200: CSR column index out of range");
   if (st & 1) throw std::runtime_error("propack_b200: CSR column indices must be sorted within each row");
-  finish_operand<T>(c, op->A, m, n, nnz, op->rp.p, op->ci.p, op->va.p);
-  finish_operand<T>(c, op->At, n, m, nnz, op->trp.p, op->tci.p, op->tva.p);
+  // column panels whose block of the gathered vector stays L2-resident (one panel unless the vector is tens of MB)
+  const int Ga = column_blocks<T>(n), Gt = column_blocks<T>(m);
+  const long lda_ = shard_slice(n, Ga), ldt_ = shard_slice(m, Gt);
+  op->A.build(c, m, n, nnz, op->rp.p, op->ci.p, op->va.p, lda_, Ga, 0, Ga, kSellCtasPerSm);
+  op->At.build(c, n, m, nnz, op->trp.p, op->tci.p, op->tva.p, ldt_, Gt, 0, Gt, kSellCtasPerSm);
   OpEntry e; e.tag = abi<T>::tag; e.kind = 0; e.op = op;
   return register_op(e);
   PB_API_CATCH(return code__)
@@ -157,30 +160,12 @@ int csr_create_sharded(int mg, int ng, const int* row_rp, const int* row_ci, con
     k_rebase(c, (long)rows + 1, rp.p, base);
     k_rebase(c, nnz, ci.p, base);
     if (k_csr_check_rowptr(c, rows, nnz, rp.p)) throw std::runtime_error("propack_b200: sharded CSR row pointers must be non-decreasing");
-    auto& P = op->phases[d];
-    P.clear();
-    std::vector<int*> out_rp(G);
-    std::vector<DeviceBuffer<int>*> out_ci(G);
-    std::vector<DeviceBuffer<T>*> out_va(G);
-    std::vector<long> nnz_g(G, 0);
-    for (int g = 0; g < G; ++g) {
-      P.emplace_back(new typename ShardedCsrOperator<T>::Phase());
-      P[g]->rp.alloc((size_t)rows + 1);
-      out_rp[g] = P[g]->rp.p; out_ci[g] = &P[g]->ci; out_va[g] = &P[g]->va;
-    }
-    const int st = k_csr_split_phases<T>(c, rows, width, rp.p, ci.p, va.p, ld, cm.world, cm.rank, G, out_rp.data(), out_ci.data(),
-                                         out_va.data(), nnz_g.data());
+    // one CTA slot per SM stays free, so that the NVLink push kernel of the side stream can always become resident while
+    // the SpMV CTAs spin on arrival flags
+    const int st = op->sets[d].build(c, rows, ld * cm.world, nnz, rp.p, ci.p, va.p, ld, cm.world, cm.rank, G, /*all resident slots but one*/ -1);
     if (st & 2) throw std::runtime_error("propack_b200: sharded CSR index out of range");
     if (st & 1) throw std::runtime_error("propack_b200: CSR indices must be sorted within each row");
-    const int per = cm.world / G;
-    for (int g = 0; g < G; ++g) {
-      finish_operand<T>(c, P[g]->S, rows, (int)(ld * cm.world), nnz_g[g], P[g]->rp.p, P[g]->ci.p, P[g]->va.p);
-      P[g]->src_mask = 0;
-      for (int k = g * per; k < (g + 1) * per; ++k) {
-        const int src = ((cm.rank - k) % cm.world + cm.world) % cm.world;
-        if (src != cm.rank) P[g]->src_mask |= 1u << src;
-      }
-    }
+    (void)width;
   };
   upload(0, ml, ng, op->ld_n, row_rp, row_ci, row_va);
   upload(1, nl, mg, op->ld_m, colt_rp, colt_ci, colt_va);
@@ -873,44 +858,50 @@ int propack_b200_csr_get_transpose(int handle, int* t_rowptr, int* t_colind, voi
     using T = std::remove_pointer_t<decltype(t)>;
     auto* op = static_cast<CsrOperator<T>*>(e.op.get());
     PB_CUDA(cudaMemcpy(t_rowptr, op->trp.p, sizeof(int) * (op->n + 1), cudaMemcpyDeviceToHost));
-    if (op->A.csr.nnz) {
-      PB_CUDA(cudaMemcpy(t_colind, op->tci.p, sizeof(int) * op->A.csr.nnz, cudaMemcpyDeviceToHost));
-      PB_CUDA(cudaMemcpy(t_values, op->tva.p, sizeof(T) * op->A.csr.nnz, cudaMemcpyDeviceToHost));
+    if (op->A.nnz) {
+      PB_CUDA(cudaMemcpy(t_colind, op->tci.p, sizeof(int) * op->A.nnz, cudaMemcpyDeviceToHost));
+      PB_CUDA(cudaMemcpy(t_values, op->tva.p, sizeof(T) * op->A.nnz, cudaMemcpyDeviceToHost));
     }
     return 0;
   });
   PB_API_CATCH(return code__)
 }
 
-// SELL-32-sigma copy of a registered CSR operator (adjoint = 1: of A^T): sizes, then the arrays (integer work, bit-exact
-// against the numpy restatement in tests/sell_ref.py).  info[0..3] = slices, stored entries incl. padding, sigma, long-row threshold.
-int propack_b200_csr_sell_info(int handle, int adjoint, long long* info4) {
+// Sliced jagged-ELL copy of a registered CSR operator (adjoint = 1: of A^T; panel = column block): sizes, then the arrays
+// (integer work, bit-exact against the numpy restatement in tests/sell_ref.py).
+// info[0..3] = slices, stored entries, number of panels, long-row threshold.
+int propack_b200_csr_sell_info(int handle, int adjoint, int panel, long long* info4) {
   PB_API_TRY
   OpEntry e = find_op(handle);
   if (e.kind != 0) throw std::runtime_error("propack_b200: not a CSR operator handle");
   return dispatch(e.tag, [&](auto* t) {
     using T = std::remove_pointer_t<decltype(t)>;
     auto* op = static_cast<CsrOperator<T>*>(e.op.get());
-    const SellDevice<T>& S = (adjoint ? op->At : op->A).sell.dev;
-    info4[0] = S.nslices; info4[1] = S.padded; info4[2] = kSellSigma; info4[3] = kSellLong;
+    PanelSet<T>& P = adjoint ? op->At : op->A;
+    if (panel < 0 || panel >= (int)P.panels.size()) throw std::runtime_error("propack_b200: no such panel");
+    const SellDevice<T>& S = P.panels[panel]->S.sell.dev;
+    info4[0] = S.nslices; info4[1] = S.stored; info4[2] = (long long)P.panels.size(); info4[3] = kSellLong;
     return 0;
   });
   PB_API_CATCH(return code__)
 }
-int propack_b200_csr_get_sell(int handle, int adjoint, long long* slice_offsets, int* perm, int* colind, void* values) {
+int propack_b200_csr_get_sell(int handle, int adjoint, int panel, long long* slice_offsets, unsigned char* row_len, int* colind,
+                              void* values) {
   PB_API_TRY
   OpEntry e = find_op(handle);
   if (e.kind != 0) throw std::runtime_error("propack_b200: not a CSR operator handle");
   return dispatch(e.tag, [&](auto* t) {
     using T = std::remove_pointer_t<decltype(t)>;
     auto* op = static_cast<CsrOperator<T>*>(e.op.get());
-    const SellDevice<T>& S = (adjoint ? op->At : op->A).sell.dev;
-    if (S.soff == nullptr) throw std::runtime_error("propack_b200: the operator has no SELL copy (PROPACK_B200_SPMV=csr)");
-    PB_CUDA(cudaMemcpy(slice_offsets, S.soff, sizeof(long long) * (S.nslices + 1), cudaMemcpyDeviceToHost));
-    PB_CUDA(cudaMemcpy(perm, S.perm, sizeof(int) * S.nslices * 32, cudaMemcpyDeviceToHost));
-    if (S.padded) {
-      PB_CUDA(cudaMemcpy(colind, S.ci, sizeof(int) * S.padded, cudaMemcpyDeviceToHost));
-      PB_CUDA(cudaMemcpy(values, S.va, sizeof(T) * S.padded, cudaMemcpyDeviceToHost));
+    PanelSet<T>& P = adjoint ? op->At : op->A;
+    if (panel < 0 || panel >= (int)P.panels.size()) throw std::runtime_error("propack_b200: no such panel");
+    const SellDevice<T>& S = P.panels[panel]->S.sell.dev;
+    if (S.joff == nullptr) throw std::runtime_error("propack_b200: the operator has no jagged-ELL copy (PROPACK_B200_SPMV=csr)");
+    PB_CUDA(cudaMemcpy(slice_offsets, S.joff, sizeof(long long) * (S.nslices + 1), cudaMemcpyDeviceToHost));
+    if (S.rows) PB_CUDA(cudaMemcpy(row_len, S.len8, (size_t)S.rows, cudaMemcpyDeviceToHost));
+    if (S.stored) {
+      PB_CUDA(cudaMemcpy(colind, S.ci, sizeof(int) * S.stored, cudaMemcpyDeviceToHost));
+      PB_CUDA(cudaMemcpy(values, S.va, sizeof(T) * S.stored, cudaMemcpyDeviceToHost));
     }
     return 0;
   });
@@ -1118,6 +1109,7 @@ int propack_b200_set_option(const char* name, int value) {
   throw std::runtime_error("propack_b200: unknown option '" + n + "'");
   PB_API_CATCH(return code__)
 }
+void propack_b200_release_cache(void) { try { Context& c = Context::get(); c.sync(); c.basis_cache_clear(); } catch (...) {} }
 void propack_b200_set_profile(int on) { try { Context::get().profile = on != 0; } catch (...) {} }
 void propack_b200_reset_counters(void) { try { Context::get().ctr = Counters(); } catch (...) {} }
 void propack_b200_get_counters(long long* out) {

@@ -108,6 +108,32 @@ void* Context::scratch(size_t bytes) {
   return scratch_;
 }
 
+void* Context::basis_acquire(const BasisLayout& lay, bool* zeroed) {
+  for (size_t i = 0; i < parked_.size(); ++i)
+    if (parked_[i].lay == lay) {
+      void* p = parked_[i].p;
+      parked_.erase(parked_.begin() + i);
+      *zeroed = true;
+      return p;
+    }
+  // another layout: the parked buffers would only pin memory the new solve needs
+  basis_cache_clear();
+  void* p = nullptr;
+  const size_t bytes = (size_t)lay.ld * (size_t)lay.cols * (size_t)lay.elem;
+  PB_CUDA(cudaMalloc(&p, bytes ? bytes : 16));
+  *zeroed = false;
+  return p;
+}
+void Context::basis_release(void* p, const BasisLayout& lay) {
+  if (!p) return;
+  if (parked_.size() >= 2 || std::getenv("PROPACK_B200_NO_BASIS_CACHE")) { cudaFree(p); return; }
+  parked_.push_back(Parked{p, lay});
+}
+void Context::basis_cache_clear() {
+  for (auto& b : parked_) cudaFree(b.p);
+  parked_.clear();
+}
+
 Context::PhaseScope::PhaseScope(Context& c_, Phase p) : c(c_), ph(p), l0(c_.ctr.launches) {
   if (c.profile) {
     PB_CUDA(cudaEventCreate(&e0));

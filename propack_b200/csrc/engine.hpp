@@ -61,8 +61,8 @@ template <class T> struct LinOp {
   virtual void invalidate_staged() {}
 };
 
-// One sparse operand in its two device forms: the caller's CSR (kept: the long-row kernel and the transpose export read
-// it; PROPACK_B200_SPMV=csr also runs the whole product from it) and the SELL-32-sigma copy the default kernel streams.
+// One sparse operand in its two device forms: the CSR arrays (kept: the long-row kernel and the transpose export read
+// them; PROPACK_B200_SPMV=csr also runs the whole product from them) and the sliced jagged-ELL copy the default kernel streams.
 template <class T> struct SparseOperand {
   CsrDevice<T> csr;
   SellStorage<T> sell;
@@ -76,7 +76,8 @@ inline bool spmv_use_sell() {
 
 // CSR arrays already on the device (0-based, validated) -> long-row list, lanes-per-row of the CSR kernel, SELL copy
 template <class T>
-void finish_operand(Context& c, SparseOperand<T>& S, int rows, int cols, long nnz, const int* rp, const int* ci, const T* va) {
+void finish_operand(Context& c, SparseOperand<T>& S, int rows, int cols, long nnz, const int* rp, const int* ci, const T* va,
+                    int ctas_per_sm = kSellCtasPerSm) {
   CsrDevice<T>& D = S.csr;
   D.rows = rows; D.cols = cols; D.nnz = nnz; D.rp = rp; D.ci = ci; D.va = va;
   const bool sell = spmv_use_sell();
@@ -84,27 +85,108 @@ void finish_operand(Context& c, SparseOperand<T>& S, int rows, int cols, long nn
   D.long_rows = D.n_long ? S.long_rows.p : nullptr;
   D.lpr_log2 = csr_lanes_per_row_log2(nnz, rows, spmv_group_nnz<T>());
   if (const char* e = std::getenv("PROPACK_B200_SPMV_LPR_LOG2")) D.lpr_log2 = std::min(5, std::max(0, std::atoi(e)));
-  if (sell) sell_build<T>(c, rows, cols, nnz, rp, ci, va, S.sell);
+  if (sell) sell_build<T>(c, rows, cols, nnz, rp, ci, va, S.sell, ctas_per_sm);
 }
 
-template <class T> double operand_bytes(const SparseOperand<T>& S) {   // SURVEY 8d byte model of one product (x counted once)
-  const double w = sizeof(T);
-  return (double)S.csr.nnz * (w + 4) + ((double)S.csr.rows + 1) * 4 + (double)S.csr.cols * w + (double)S.csr.rows * w;
+// A sparse operand split by column range into panels ("phases"): y = sum_g A_g x.  One panel = the whole operand.
+// Single GPU: the panels are L2-sized column blocks (sell.cu, "Column blocking"); row-sharded: the source ranks of the
+// gathered vector, in the order their slices arrive.
+template <class T> struct PanelSet {
+  using R = real_t<T>;
+  struct Panel {
+    DeviceBuffer<int> rp, ci;
+    DeviceBuffer<T> va;
+    SparseOperand<T> S;
+    unsigned int src_mask = 0;   // row-sharded: ranks whose slices this panel reads (own rank excluded: no wait needed)
+  };
+  std::vector<std::unique_ptr<Panel>> panels;
+  long nnz = 0;
+  int rows = 0;
+  // Split the CSR (device pointers) into G panels: panel of column c = ring distance of (c / ld) behind `rank`, / (P/G).
+  // Returns the validation status of k_csr_split_phases (0 = ok).
+  int build(Context& c, int rows_, long width, long nnz_, const int* rp, const int* ci, const T* va, long ld, int P, int rank, int G,
+            int ctas_per_sm) {
+    rows = rows_; nnz = nnz_;
+    panels.clear();
+    std::vector<int*> out_rp(G);
+    std::vector<DeviceBuffer<int>*> out_ci(G);
+    std::vector<DeviceBuffer<T>*> out_va(G);
+    std::vector<long> nnz_g(G, 0);
+    for (int g = 0; g < G; ++g) {
+      panels.emplace_back(new Panel());
+      panels[g]->rp.alloc((size_t)rows + 1);
+      out_rp[g] = panels[g]->rp.p; out_ci[g] = &panels[g]->ci; out_va[g] = &panels[g]->va;
+    }
+    const int st = k_csr_split_phases<T>(c, rows, width, rp, ci, va, ld, P, rank, G, out_rp.data(), out_ci.data(), out_va.data(),
+                                         nnz_g.data());
+    if (st) return st;
+    const int per = P / G;
+    for (int g = 0; g < G; ++g) {
+      Panel& pn = *panels[g];
+      finish_operand<T>(c, pn.S, rows, (int)width, nnz_g[g], pn.rp.p, pn.ci.p, pn.va.p, ctas_per_sm);
+      if (spmv_use_sell() && pn.S.csr.n_long == 0) {   // the jagged copy is all the kernels read: drop the panel's CSR entries
+        pn.ci.free(); pn.va.free();
+        pn.S.csr.ci = nullptr; pn.S.csr.va = nullptr;
+      }
+      pn.src_mask = 0;
+      if (P > 1 && G <= P)
+        for (int k = g * per; k < (g + 1) * per; ++k) {
+          const int src = ((rank - k) % P + P) % P;
+          if (src != rank) pn.src_mask |= 1u << src;
+        }
+    }
+    return 0;
+  }
+  // y = sum_g A_g x + coef*prev, ||y||.  flags != null: panel g first waits for the arrival flags of its sources.
+  void apply(Context& c, bool conj, const T* x, T* y, R coef, const T* prev, Pending* nrm, const unsigned long long* flags,
+             unsigned long long epoch) {
+    const size_t G = panels.size();
+    for (size_t g = 0; g < G; ++g) {
+      Panel& pn = *panels[g];
+      const unsigned int mask = flags ? pn.src_mask : 0u;
+      const bool last = g + 1 == G;
+      if (spmv_use_sell()) {
+        const int mode = (g ? kSellModeAcc : 0) | (last ? kSellModeFinal : 0);
+        if (mask && pn.S.csr.n_long > 0) k_wait_flags(c, flags, mask, epoch);   // the long-row kernel has no in-kernel wait
+        k_spmv_sell<T>(c, pn.S.sell.dev, &pn.S.csr, conj, x, y, coef, prev, last ? nrm : nullptr, mode, flags, mask, epoch);
+      } else {
+        // CSR kernel: the epilogue term goes in with the first panel, later panels add onto y
+        if (mask) k_wait_flags(c, flags, mask, epoch);
+        k_spmv<T>(c, pn.S.csr, conj, x, y, g == 0 ? coef : R(1), g == 0 ? prev : y, last ? nrm : nullptr);
+      }
+    }
+  }
+  double stream_bytes() const {   // matrix entries + row lengths / pointers + y traffic of the panel passes
+    const double w = sizeof(T);
+    return (double)nnz * (w + 4) + ((double)rows + 1) * 4 + (double)rows * w;
+  }
+};
+
+// Panels of a single-GPU operand: as many column blocks as it takes to keep one block of the gathered vector L2-resident
+// (PROPACK_B200_SPMV_COLBLOCK_MB, default 48 MB per block -- measured on config 5: two 40 MB blocks beat one 80 MB vector by 18 %
+// and four 20 MB blocks lose to the per-panel overhead; PROPACK_B200_SPMV_COLBLOCKS forces the count), at most 8.
+template <class T> inline int column_blocks(long cols) {
+  if (const char* e = std::getenv("PROPACK_B200_SPMV_COLBLOCKS")) return std::min(8, std::max(1, std::atoi(e)));
+  double mb = 48.0;
+  if (const char* e = std::getenv("PROPACK_B200_SPMV_COLBLOCK_MB")) mb = std::max(1.0, std::atof(e));
+  const double need = (double)cols * sizeof(T) / (mb * 1048576.0);
+  int G = 1;
+  while (G < 8 && G < need) G *= 2;
+  return G;
 }
 
 template <class T> struct CsrOperator : LinOp<T> {
   using R = real_t<T>;
   DeviceBuffer<int> rp, ci, trp, tci;
   DeviceBuffer<T> va, tva;
-  SparseOperand<T> A, At;  // At = A^T (values not conjugated)
+  PanelSet<T> A, At;  // At = A^T (values not conjugated)
   void apply(Context& c, bool adjoint, const T* x, T* y, R coef, const T* prev, Pending* nrm) override {
-    SparseOperand<T>& S = adjoint ? At : A;
-    if (spmv_use_sell())
-      k_spmv_sell<T>(c, S.sell.dev, &S.csr, /*conj=*/adjoint, x, y, coef, prev, nrm, kSellModeFinal, nullptr, 0u, 0ull);
-    else
-      k_spmv<T>(c, S.csr, /*conj=*/adjoint, x, y, coef, prev, nrm);
+    (adjoint ? At : A).apply(c, /*conj=*/adjoint, x, y, coef, prev, nrm, nullptr, 0ull);
   }
-  double algorithmic_bytes(bool adjoint) const override { return operand_bytes(adjoint ? At : A); }
+  double algorithmic_bytes(bool adjoint) const override {
+    const PanelSet<T>& S = adjoint ? At : A;
+    return S.stream_bytes() + (double)(adjoint ? this->m : this->n) * sizeof(T);
+  }
 };
 
 // Row-sharded CSR operator: this rank holds its row block of A (m_loc x ng) and the transpose of its column block
@@ -112,21 +194,15 @@ template <class T> struct CsrOperator : LinOp<T> {
 // inside a matvec.  Slices are contiguous and of equal padded length, so global column indices address the gathered
 // vector directly.
 //
-// Each local operand is split by the SOURCE RANK of the gathered vector into G phases (G = min(world, 4) by default,
-// PROPACK_B200_SPMV_PHASES): phase g holds the entries whose column belongs to the ranks at ring distance
+// Each local operand is split by the SOURCE RANK of the gathered vector into G panels (G = min(world, 4) by default,
+// PROPACK_B200_SPMV_PHASES): panel g holds the entries whose column belongs to the ranks at ring distance
 // [g*P/G, (g+1)*P/G) behind this rank -- the order in which the staggered push (k_scal_push) delivers the slices.
-// The product is  y = sum_g A_g x_g : phase g waits, inside its SELL kernel, only for its own sources, so the SpMV over
-// the slices that have landed overlaps the NVLink transfer of the ones still in flight.  The push runs on a few CTAs
-// of a side stream; the SpMV kernels leave it room (k_spmv_sell).
+// Panel g waits, inside its kernel, only for its own sources, so the SpMV over the slices that have landed overlaps the
+// NVLink transfer of the ones still in flight.  The push runs on a few CTAs of a side stream; the SpMV kernels leave
+// it room (one CTA slot per SM stays free).
 template <class T> struct ShardedCsrOperator : LinOp<T> {
   using R = real_t<T>;
-  struct Phase {
-    DeviceBuffer<int> rp, ci;
-    DeviceBuffer<T> va;
-    SparseOperand<T> S;
-    unsigned int src_mask = 0;   // ranks whose slices this phase reads (own rank excluded: no wait needed)
-  };
-  std::vector<std::unique_ptr<Phase>> phases[2];
+  PanelSet<T> sets[2];
   DeviceBuffer<T> xbuf[2];
   // gather buffers: [world*ld elements | kMaxRanks arrival flags]; peer windows when NVLink peer memory is mapped
   // (index 0: the n-vector gathered for A x, index 1: the m-vector gathered for A^H x)
@@ -170,32 +246,15 @@ template <class T> struct ShardedCsrOperator : LinOp<T> {
   void apply(Context& c, bool adjoint, const T* x, T* y, R coef, const T* prev, Pending* nrm) override {
     Comm& cm = Comm::get();
     const int d = adjoint ? 1 : 0;
-    // staged: the slices are being pushed by the producers (stage_scaled); each phase waits only for its own sources.
+    // staged: the slices are being pushed by the producers (stage_scaled); each panel waits only for its own sources.
     // (nrm != nullptr: the cross-rank norm reduction that follows is what makes reusing the buffer safe.)
     const bool staged = staged_valid[d] && staged_ptr[d] == x && nrm != nullptr;
     if (!staged) cm.allgather(x, xfull[d], sizeof(T) * (size_t)ld_of(d), c.stream);
     staged_valid[d] = false;
-    const size_t G = phases[d].size();
-    for (size_t g = 0; g < G; ++g) {
-      Phase& ph = *phases[d][g];
-      const unsigned int mask = staged ? ph.src_mask : 0u;
-      const int mode = (g ? kSellModeAcc : 0) | (g + 1 == G ? kSellModeFinal : 0);
-      if (spmv_use_sell()) {
-        if (mask && ph.S.csr.n_long > 0) k_wait_flags(c, flags(d), mask, epoch[d]);   // the long-row kernel has no in-kernel wait
-        k_spmv_sell<T>(c, ph.S.sell.dev, &ph.S.csr, /*conj=*/adjoint, xfull[d], y, coef, prev, g + 1 == G ? nrm : nullptr, mode,
-                       flags(d), mask, epoch[d]);
-      } else {
-        if (mask) k_wait_flags(c, flags(d), mask, epoch[d]);
-        k_spmv<T>(c, ph.S.csr, /*conj=*/adjoint, xfull[d], y, g == 0 ? coef : R(1), g == 0 ? prev : y, g + 1 == G ? nrm : nullptr);
-      }
-    }
+    sets[d].apply(c, /*conj=*/adjoint, xfull[d], y, coef, prev, nrm, staged ? flags(d) : nullptr, epoch[d]);
   }
   double algorithmic_bytes(bool adjoint) const override {
-    const double w = sizeof(T);
-    double b = 0;
-    for (const auto& ph : phases[adjoint ? 1 : 0])
-      b += (double)ph->S.csr.nnz * (w + 4) + ((double)ph->S.csr.rows + 1) * 4 + (double)ph->S.csr.rows * w;
-    return b + (double)ld_of(adjoint ? 1 : 0) * Comm::get().world * w;
+    return sets[adjoint ? 1 : 0].stream_bytes() + (double)ld_of(adjoint ? 1 : 0) * Comm::get().world * sizeof(T);
   }
 };
 
@@ -253,8 +312,9 @@ template <class T> class Engine {
   bool dist;          // row-sharded run: reductions are completed across ranks
   long ldu, ldv;      // padded leading dimensions (multiples of 32 elements => 256-byte aligned columns)
   int ucols, vcols;   // allocated columns
-  DeviceBuffer<T> Ubuf, Vbuf, wrk, hbuf;
+  DeviceBuffer<T> wrk, hbuf;
   T* U; T* V;
+  Context::BasisLayout ulay, vlay;
 
   static long pad_ld(long rows) { return (rows + 31) / 32 * 32; }
 
@@ -262,16 +322,26 @@ template <class T> class Engine {
       : c(ctx), op(op_), m(op_->m), n(op_->n), mg(op_->global_m()), ng(op_->global_n()),
         dist(op_->sharded && Comm::get().active()), ldu(op_->ld_m > 0 ? op_->ld_m : pad_ld(op_->m)),
         ldv(op_->ld_n > 0 ? op_->ld_n : pad_ld(op_->n)), ucols(ucols_), vcols(vcols_) {
-    Ubuf.alloc((size_t)ldu * ucols);
-    Vbuf.alloc((size_t)ldv * vcols);
     wrk.alloc((size_t)std::max(ldu, ldv));
     hbuf.alloc((size_t)std::max(ucols, vcols) + 8);
-    U = Ubuf.p; V = Vbuf.p;
-    // padding rows must be (and stay) zero: kernels read whole 128-bit packs past the last row
-    PB_CUDA(cudaMemsetAsync(U, 0, sizeof(T) * (size_t)ldu * ucols, c.stream));
-    PB_CUDA(cudaMemsetAsync(V, 0, sizeof(T) * (size_t)ldv * vcols, c.stream));
+    // padding rows must be (and stay) zero: kernels read whole 128-bit packs past the last row.  Recycled basis buffers
+    // of the same layout already satisfy that (Context::basis_acquire).
+    ulay.ld = ldu; ulay.cols = ucols; ulay.elem = (int)sizeof(T);
+    vlay.ld = ldv; vlay.cols = vcols; vlay.elem = (int)sizeof(T);
+    bool uz = false, vz = false;
+    U = static_cast<T*>(c.basis_acquire(ulay, &uz));
+    V = static_cast<T*>(c.basis_acquire(vlay, &vz));
+    if (!uz) PB_CUDA(cudaMemsetAsync(U, 0, sizeof(T) * (size_t)ldu * ucols, c.stream));
+    if (!vz) PB_CUDA(cudaMemsetAsync(V, 0, sizeof(T) * (size_t)ldv * vcols, c.stream));
     PB_CUDA(cudaMemsetAsync(wrk.p, 0, sizeof(T) * wrk.n, c.stream));
   }
+  ~Engine() {
+    cudaStreamSynchronize(c.stream);
+    c.basis_release(U, ulay);
+    c.basis_release(V, vlay);
+  }
+  Engine(const Engine&) = delete;
+  Engine& operator=(const Engine&) = delete;
   // While alive, kernels launched through this engine publish cross-rank reductions (no-op on one GPU).
   struct DistScope {
     Context& c; bool old;

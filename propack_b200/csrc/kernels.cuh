@@ -65,29 +65,38 @@ void k_spmv(Context& c, const CsrDevice<T>& A, bool conj, const T* x, T* y, real
 template <class T>
 void k_spmv_long(Context& c, const CsrDevice<T>& A, bool conj, const T* x, T* y, real_t<T> coef, const T* prev, bool accumulate);
 
-// --- sliced-ELL (SELL-32-sigma) SpMV, the default sparse APROD kernel (sell.cu) -----------------------------------
-constexpr int kSellSigma = 1024;     // rows per sorting window (rows are sorted by length inside a window)
+// --- sliced jagged-ELL SpMV, the default sparse APROD kernel (sell.cu) ------------------------------------------------
 constexpr int kSellLong = 64;        // rows longer than this go to spmv_long_kernel (one CTA per row)
-constexpr int kSellCtasPerSm = 5;    // persistent CTAs per SM (no shared memory: L1 keeps the whole 228 KB)
+constexpr int kSellCtasPerSm = 8;    // upper bound on persistent CTAs per SM; the builder caps it by the kernel's real occupancy
+constexpr int kSellStepCost = 4;     // weight of one k-step of a slice (coalesced ci / va loads), in gathered entries
+constexpr int kSellSliceCost = 8;    // fixed weight of a slice (lengths, y / prev access, epilogue)
 template <class T> struct SellDevice {
   int rows = 0, cols = 0;
   long nnz = 0;
-  long nslices = 0;                // 32-row slices (a multiple of kSellSigma/32; trailing slots carry perm = -1)
-  long long padded = 0;            // stored entries incl. padding
-  const long long* soff = nullptr; // [nslices+1] first entry of each slice (multiples of 32)
-  const int* perm = nullptr;       // [nslices*32] original row of a slot | 0x40000000 if the row is "long"; -1 = no row
-  const int* ci = nullptr;         // [padded] column, -1 = padding
-  const T* va = nullptr;           // [padded]
+  long nslices = 0;                   // 32-row slices: ceil(rows / 32)
+  long long stored = 0;               // entries in the slices (= nnz minus the long rows' entries)
+  const long long* joff = nullptr;    // [nslices+1] first stored entry of each slice
+  const unsigned char* len8 = nullptr;// [rows] row length, 0xFF = long row (done by spmv_long_kernel)
+  const int* ci = nullptr;            // [stored] columns, k-major compacted inside a slice
+  const T* va = nullptr;              // [stored]
+  // static load balance: warp w of the planned grid owns the contiguous slices [wstart[w], wstart[w+1]) -- equal shares of
+  // sum(entries + kSellStepCost*longest row + kSellSliceCost) -- so ragged slices do not pile up on some warps
+  const int* wstart = nullptr;        // [grid*8 + 1]
+  int grid = 0;                       // CTAs the partition was made for (the kernel is launched with exactly this grid)
 };
 template <class T> struct SellStorage {
-  DeviceBuffer<long long> soff;
-  DeviceBuffer<int> perm, ci;
+  DeviceBuffer<long long> joff;
+  DeviceBuffer<unsigned char> len8;
+  DeviceBuffer<int> ci, wstart;
   DeviceBuffer<T> va;
   SellDevice<T> dev;
 };
-// CSR (device pointers, 0-based, sorted rows) -> SELL-32-sigma.  Integer work, deterministic.
+// CSR (device pointers, 0-based, sorted rows) -> sliced jagged ELL.  Integer work, deterministic.  ctas_per_sm: size of
+// the persistent grid the warp partition is planned for (> 0: at most that many, capped by the kernel's occupancy;
+// <= 0: every resident slot but -ctas_per_sm).
 template <class T>
-void sell_build(Context& c, int rows, int cols, long nnz, const int* rp, const int* ci, const T* va, SellStorage<T>& out);
+void sell_build(Context& c, int rows, int cols, long nnz, const int* rp, const int* ci, const T* va, SellStorage<T>& out,
+                int ctas_per_sm = kSellCtasPerSm);
 // y <- [y +] op(S) x [+ coef*prev ; publish ||y||].  mode: bit 0 = accumulate into y, bit 1 = final phase (epilogue).
 // long_src: the CSR whose long_rows list spmv_long_kernel serves (final phase only), or null.
 // flags/src_mask/epoch: row-sharded runs -- wait in-kernel until the gather-buffer slices of the ranks in src_mask

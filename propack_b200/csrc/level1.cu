@@ -221,9 +221,10 @@ template <class T> void k_scal(Context& c, long n, T* x, real_t<T> a) {
   PB_LAUNCH_CHECK();
   c.ctr.launches += 1;
 }
-inline int push_ctas() {
-  static const int n = [] { const char* e = std::getenv("PROPACK_B200_PUSH_CTAS"); int v = e ? std::atoi(e) : 32; return std::min(148, std::max(1, v)); }();
-  return n;
+inline int push_ctas() {   // read at every call: cheap, and lets one process compare settings
+  const char* e = std::getenv("PROPACK_B200_PUSH_CTAS");
+  const int v = e ? std::atoi(e) : 32;
+  return std::min(148, std::max(1, v));
 }
 template <class T>
 void k_scal_push(Context& c, long n, long ld, T* x, real_t<T> a, void** bases_dev, int rank, int world, unsigned long long epoch,

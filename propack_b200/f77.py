@@ -401,14 +401,16 @@ def zero(x, incx=1):
     return xb
 
 
-def sell_arrays(op: Operator, adjoint=False):
-    """The SELL-32-sigma copy of a registered CSR operator: dict(soff, perm, ci, va, sigma, long)."""
+def sell_arrays(op: Operator, adjoint=False, panel=0):
+    """The sliced jagged-ELL copy of a registered CSR operator (one column panel of it): dict(joff, len8, ci, va, panels, long)."""
     info = (C.c_longlong * 4)()
-    check(lib().propack_b200_csr_sell_info(C.c_int(op.handle), C.c_int(int(adjoint)), info), "csr_sell_info")
-    ns, padded = int(info[0]), int(info[1])
-    soff = np.zeros(ns + 1, dtype=np.int64)
-    perm = np.zeros(ns * 32, dtype=np.int32)
-    ci = np.zeros(max(padded, 1), dtype=np.int32)
-    va = np.zeros(max(padded, 1), dtype=op.dtype)
-    check(lib().propack_b200_csr_get_sell(C.c_int(op.handle), C.c_int(int(adjoint)), _p(soff), _p(perm), _p(ci), _p(va)), "csr_get_sell")
-    return dict(soff=soff, perm=perm, ci=ci[:padded], va=va[:padded], sigma=int(info[2]), long=int(info[3]))
+    check(lib().propack_b200_csr_sell_info(C.c_int(op.handle), C.c_int(int(adjoint)), C.c_int(panel), info), "csr_sell_info")
+    ns, stored = int(info[0]), int(info[1])
+    rows = op.shape[1] if adjoint else op.shape[0]
+    joff = np.zeros(ns + 1, dtype=np.int64)
+    len8 = np.zeros(max(rows, 1), dtype=np.uint8)
+    ci = np.zeros(max(stored, 1), dtype=np.int32)
+    va = np.zeros(max(stored, 1), dtype=op.dtype)
+    check(lib().propack_b200_csr_get_sell(C.c_int(op.handle), C.c_int(int(adjoint)), C.c_int(panel), _p(joff), _p(len8), _p(ci), _p(va)),
+          "csr_get_sell")
+    return dict(joff=joff, len8=len8[:rows], ci=ci[:stored], va=va[:stored], panels=int(info[2]), long=int(info[3]))

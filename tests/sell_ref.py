@@ -1,51 +1,58 @@
-"""numpy restatement of the SELL-32-sigma construction (propack_b200/csrc/sell.cu: sell_sort_kernel, sell_fill_kernel).
+"""numpy restatement of the sliced jagged-ELL construction (propack_b200/csrc/sell.cu: sell_lengths_kernel, sell_fill_kernel)
+and of the column-panel split (csrc/csr_build.cu: k_csr_split_phases).
 
-Test infrastructure (integer work must be bit-exact): rows are sorted by effective length (descending, stable) inside
-windows of `sigma` consecutive rows; a row longer than `long_thr` has effective length 0 and is flagged 0x40000000;
-slots past the last row carry -1; a slice is 32 consecutive slots, as wide as its first (= longest) row; entry k of slot
-l of slice s lives at soff[s] + 32*k + l; padding is (column -1, value 0).
+Test infrastructure (integer work must be bit-exact).  Rows keep their order; a slice is 32 consecutive rows; a row longer
+than `long_thr` is left out (length byte 0xFF); inside a slice the stored entries are "k-major, compacted": first the 0-th
+entry of every row that has one, in row order, then the 1-st entries, and so on.
 """
 import numpy as np
+import scipy.sparse as sp
 
 
-def sell_ref(A, sigma=1024, long_thr=64):
+def sell_ref(A, long_thr=64):
     indptr, indices, data = np.asarray(A.indptr, dtype=np.int64), np.asarray(A.indices), np.asarray(A.data)
     rows = A.shape[0]
-    nwin = (rows + sigma - 1) // sigma
-    nslices = nwin * (sigma // 32)
+    nslices = (rows + 31) // 32
     lens = np.diff(indptr)
     is_long = lens > long_thr
+    len8 = np.where(is_long, 0xFF, lens).astype(np.uint8)
     eff = np.where(is_long, 0, lens)
-    eff_pad = np.full(nwin * sigma, -1, dtype=np.int64)
-    eff_pad[:rows] = eff
-    perm = np.full(nwin * sigma, -1, dtype=np.int32)
-    len_sorted = np.zeros(nwin * sigma, dtype=np.int64)
-    for w in range(nwin):
-        seg = eff_pad[w * sigma:(w + 1) * sigma]
-        order = np.argsort(-seg, kind="stable")
-        rows_w = w * sigma + order
-        valid = seg[order] >= 0
-        p = np.where(valid, rows_w, -1).astype(np.int64)
-        flag = np.zeros(sigma, dtype=np.int64)
-        flag[valid] = np.where(is_long[rows_w[valid]], 0x40000000, 0)
-        perm[w * sigma:(w + 1) * sigma] = np.where(valid, p | flag, -1).astype(np.int32)
-        len_sorted[w * sigma:(w + 1) * sigma] = np.maximum(seg[order], 0)
-    width = len_sorted[::32]
-    soff = np.zeros(nslices + 1, dtype=np.int64)
-    soff[1:] = np.cumsum(32 * width)
-    padded = int(soff[-1])
-    ci = np.full(padded, -1, dtype=np.int32)
-    va = np.zeros(padded, dtype=data.dtype)
+    pad = np.zeros(nslices * 32, dtype=np.int64)
+    pad[:rows] = eff
+    count = pad.reshape(nslices, 32).sum(axis=1)
+    joff = np.zeros(nslices + 1, dtype=np.int64)
+    joff[1:] = np.cumsum(count)
+    stored = int(joff[-1])
+    ci = np.zeros(stored, dtype=np.int32)
+    va = np.zeros(stored, dtype=data.dtype)
     for s in range(nslices):
-        w = int(width[s])
-        if w == 0:
+        r0, r1 = s * 32, min(rows, s * 32 + 32)
+        le = eff[r0:r1]
+        if le.size == 0 or le.max() == 0:
             continue
-        for l in range(32):
-            r = int(perm[s * 32 + l])
-            if r < 0 or (r & 0x40000000):
-                continue
-            beg, ln = int(indptr[r]), int(lens[r])
-            idx = soff[s] + 32 * np.arange(ln) + l
-            ci[idx] = indices[beg:beg + ln]
-            va[idx] = data[beg:beg + ln]
-    return dict(soff=soff, perm=perm, ci=ci, va=va)
+        p = int(joff[s])
+        for k in range(int(le.max())):
+            act = np.nonzero(le > k)[0]
+            src = indptr[r0 + act] + k
+            ci[p:p + act.size] = indices[src]
+            va[p:p + act.size] = data[src]
+            p += act.size
+    return dict(joff=joff, len8=len8, ci=ci, va=va)
+
+
+def column_panels(A, G):
+    """The G column blocks of a single-GPU operand, in panel order: block width = ceil(cols / G) rounded up to 32 columns,
+    panel g = the block at ring distance g behind block 0 (block 0, then G-1, G-2, ..., 1), column ids stay global."""
+    A = sp.csr_array(A)
+    n = A.shape[1]
+    per = (n + G - 1) // G
+    ld = (per + 31) // 32 * 32
+    out = []
+    for g in range(G):
+        owner = (G - g) % G
+        lo, hi = min(owner * ld, n), min((owner + 1) * ld, n)
+        keep = (A.indices >= lo) & (A.indices < hi)
+        cs = np.concatenate([[0], np.cumsum(keep.astype(np.int64))])
+        indptr = cs[A.indptr]
+        out.append(sp.csr_array((A.data[keep], A.indices[keep], indptr), shape=A.shape))
+    return out

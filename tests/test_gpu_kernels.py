@@ -218,12 +218,12 @@ def test_safescal(oracle, dtype):
 
 
 # ---------------------------------------------------------------------------------------------------------
-# SELL-32-sigma construction (integer work: bit-exact) and the SELL SpMV on awkward shapes
+# sliced jagged-ELL construction and column-panel split (integer work: bit-exact), SpMV on awkward shapes
 # ---------------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("dtype", [np.float64, np.complex128])
 @pytest.mark.parametrize("shape", [(700, 3100), (2500, 900), (1024, 64)])
 def test_sell_build_is_bit_exact(dtype, shape):
-    """The device-built SELL copies of A and A^T equal the numpy restatement (tests/sell_ref.py) array for array."""
+    """The device-built jagged-ELL copies of A and A^T equal the numpy restatement (tests/sell_ref.py) array for array."""
     from propack_b200 import f77
     from sell_ref import sell_ref
     rng = np.random.default_rng(2)
@@ -233,12 +233,50 @@ def test_sell_build_is_bit_exact(dtype, shape):
     At.sort_indices()
     for adjoint, M in ((False, A), (True, At)):
         got = f77.sell_arrays(op, adjoint)
-        want = sell_ref(M, sigma=got["sigma"], long_thr=got["long"])
-        assert np.array_equal(got["soff"], want["soff"])
-        assert np.array_equal(got["perm"], want["perm"])
-        assert np.array_equal(got["ci"], want["ci"])
-        assert np.array_equal(got["va"], want["va"])
+        assert got["panels"] == 1
+        want = sell_ref(M, long_thr=got["long"])
+        for key in ("joff", "len8", "ci", "va"):
+            assert np.array_equal(got[key], want[key]), key
     op.close()
+
+
+def test_column_panels_are_bit_exact_and_products_agree(oracle):
+    """Column blocking (operands whose gathered vector outgrows L2; forced here with PROPACK_B200_SPMV_COLBLOCKS): every panel's
+    jagged-ELL copy equals the numpy restatement, and the panel-by-panel product equals the one-panel product's oracle value."""
+    import subprocess, sys, os, textwrap
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = textwrap.dedent("""
+        import sys, numpy as np, scipy.sparse as sp
+        sys.path.insert(0, %r); sys.path.insert(0, %r)
+        from propack_b200 import f77
+        from sell_ref import sell_ref, column_panels
+        from oracle import oracle_py as O
+        from test_gpu_kernels import ragged_matrix, rel
+        from conftest import rand_vec
+        rng = np.random.default_rng(6)
+        for dtype in (np.float64, np.complex128):
+            A = ragged_matrix(rng, 3000, 2600, dtype)
+            At = sp.csr_array(A.T); At.sort_indices()
+            op = f77.Operator(A)
+            for adjoint, M in ((False, A), (True, At)):
+                want = column_panels(M, 4)
+                for g in range(4):
+                    got = f77.sell_arrays(op, adjoint, panel=g)
+                    assert got["panels"] == 4
+                    ref = sell_ref(want[g], long_thr=got["long"])
+                    for key in ("joff", "len8", "ci", "va"):
+                        assert np.array_equal(got[key], ref[key]), (adjoint, g, key)
+            cplx = np.iscomplexobj(A.data)
+            for transa in ("n", "c" if cplx else "t"):
+                x = rand_vec(rng, A.shape[1] if transa == "n" else A.shape[0], dtype)
+                assert rel(f77.aprod(op, transa, x), O.csr_aprod(transa, A, x, dtype=dtype)) < 1e-12
+            op.close()
+        print("PANELS_OK")
+    """ % (root, os.path.join(root, "tests")))
+    p = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600,
+                       env=dict(os.environ, PROPACK_B200_SPMV_COLBLOCKS="4"))
+    sys.stdout.write(p.stdout[-2000:]); sys.stderr.write(p.stderr[-3000:])
+    assert p.returncode == 0 and "PANELS_OK" in p.stdout
 
 
 @pytest.mark.parametrize("dtype", DTYPES)
