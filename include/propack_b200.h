@@ -237,8 +237,9 @@ void printstat_(void);
  * (2) device-resident operators (new; the GPU addendum of SURVEY.md section 8b)
  * ===================================================================================================== */
 
-/* Register an m x n CSR matrix (host arrays, 0- or 1-based indices, int32).  The library uploads it and
- * builds the CSR of A^T on the device.  Returns a handle > 0, or a negative error code. */
+/* Register an m x n CSR matrix (0- or 1-based indices, int32; the three arrays may be host pointers or pointers into this
+ * device's memory, e.g. a torch CSR tensor).  The library copies it and builds the CSR of A^T and the kernel-side
+ * layouts on the device.  Returns a handle > 0, or a negative error code. */
 int propack_b200_csr_create_s(int m, int n, const int* rowptr, const int* colind, const float* values, int index_base);
 int propack_b200_csr_create_d(int m, int n, const int* rowptr, const int* colind, const double* values, int index_base);
 int propack_b200_csr_create_c(int m, int n, const int* rowptr, const int* colind, const pb200_complex8* values, int index_base);
@@ -259,7 +260,10 @@ int propack_b200_dense_create_s(int m, int n, const float* A, long lda);
 int propack_b200_dense_create_d(int m, int n, const double* A, long lda);
 int propack_b200_dense_create_c(int m, int n, const pb200_complex8* A, long lda);
 int propack_b200_dense_create_z(int m, int n, const pb200_complex16* A, long lda);
+int propack_b200_dense_adopt_device_s(int m, int n, const float* A_device, long lda);
 int propack_b200_dense_adopt_device_d(int m, int n, const double* A_device, long lda);
+int propack_b200_dense_adopt_device_c(int m, int n, const pb200_complex8* A_device, long lda);
+int propack_b200_dense_adopt_device_z(int m, int n, const pb200_complex16* A_device, long lda);
 /* synthetic dense operator generated on the device (BASELINE config 3: 2M x 4096 = 65.5 GB never exists on the host):
  * A(i,j) = u(i,j) + sum_g table[g][byte_g(X(i)^Y(j))], see csrc/dense_gen.cu and propack_b200/synth.py (bit-identical
  * numpy replica for parity tests).  Plays the role of the user's APROD data (double/dlansvd.F:20-33). */

@@ -91,18 +91,22 @@ template <class T> int csr_create(int m, int n, const int* rowptr, const int* co
   Context& c = Context::get();
   const T* values = static_cast<const T*>(values_);
   if (m <= 0 || n <= 0 || !rowptr || !colind || !values) throw std::runtime_error("propack_b200: bad CSR arguments");
-  const long nnz = (long)rowptr[m] - base;
-  if (rowptr[0] != base || nnz < 0) throw std::runtime_error("propack_b200: CSR row pointers do not start at the index base");
+  // the three arrays may live on the host or on this device (e.g. a torch CSR tensor): cudaMemcpyDefault copies either
+  int rp_ends[2] = {0, 0};
+  PB_CUDA(cudaMemcpy(&rp_ends[0], rowptr, sizeof(int), cudaMemcpyDefault));
+  PB_CUDA(cudaMemcpy(&rp_ends[1], rowptr + m, sizeof(int), cudaMemcpyDefault));
+  const long nnz = (long)rp_ends[1] - base;
+  if (rp_ends[0] != base || nnz < 0) throw std::runtime_error("propack_b200: CSR row pointers do not start at the index base");
   auto op = std::make_shared<CsrOperator<T>>();
   op->m = m; op->n = n;
   op->rp.alloc(m + 1); op->ci.alloc(std::max<long>(nnz, 1)); op->va.alloc(std::max<long>(nnz, 1));
   op->trp.alloc(n + 1); op->tci.alloc(std::max<long>(nnz, 1)); op->tva.alloc(std::max<long>(nnz, 1));
   // the three host arrays go up as they are; re-basing, validation (row pointers, column range, sorted rows), the
   // canonical transpose and the SELL copies are all built on the device (csr_build.cu, sell.cu)
-  PB_CUDA(cudaMemcpyAsync(op->rp.p, rowptr, sizeof(int) * (m + 1), cudaMemcpyHostToDevice, c.stream));
+  PB_CUDA(cudaMemcpyAsync(op->rp.p, rowptr, sizeof(int) * (m + 1), cudaMemcpyDefault, c.stream));
   if (nnz) {
-    PB_CUDA(cudaMemcpyAsync(op->ci.p, colind, sizeof(int) * nnz, cudaMemcpyHostToDevice, c.stream));
-    PB_CUDA(cudaMemcpyAsync(op->va.p, values, sizeof(T) * nnz, cudaMemcpyHostToDevice, c.stream));
+    PB_CUDA(cudaMemcpyAsync(op->ci.p, colind, sizeof(int) * nnz, cudaMemcpyDefault, c.stream));
+    PB_CUDA(cudaMemcpyAsync(op->va.p, values, sizeof(T) * nnz, cudaMemcpyDefault, c.stream));
   }
   k_rebase(c, m + 1, op->rp.p, base);
   k_rebase(c, nnz, op->ci.p, base);
@@ -811,8 +815,13 @@ void printstat_(void) {  // layout follows double/printstat.F:35-75
 }
 
 // ---- operators ------------------------------------------------------------------------------------------
-int propack_b200_dense_adopt_device_d(int m, int n, const double* A_device, long lda) {
-  return dense_create<double>(m, n, A_device, lda, true);
+int propack_b200_dense_adopt_device_s(int m, int n, const float* A_device, long lda) { return dense_create<float>(m, n, A_device, lda, true); }
+int propack_b200_dense_adopt_device_d(int m, int n, const double* A_device, long lda) { return dense_create<double>(m, n, A_device, lda, true); }
+int propack_b200_dense_adopt_device_c(int m, int n, const pb200_complex8* A_device, long lda) {
+  return dense_create<cplx<float>>(m, n, A_device, lda, true);
+}
+int propack_b200_dense_adopt_device_z(int m, int n, const pb200_complex16* A_device, long lda) {
+  return dense_create<cplx<double>>(m, n, A_device, lda, true);
 }
 int propack_b200_dense_create_synthetic_d(int m, int n, unsigned long long seed, const double* table16x256) {
   PB_API_TRY

@@ -117,10 +117,13 @@ class Context {
   // Basis-buffer cache.  The Fortran-ABI drivers own no state between calls, but allocating and zeroing the Krylov
   // bases (2 x 24 GB on BASELINE config 5) on every call is pure overhead for a caller that solves repeatedly: a
   // released basis buffer is parked here and handed back, WITHOUT a memset, to the next request with the same layout
-  // (leading dimension, column count, element size) -- every kernel keeps the padding rows zero and the drivers overwrite
+  // (leading dimension, valid rows, column count, element size) -- every kernel keeps the padding rows zero and the drivers overwrite
   // each column before reading it, so a recycled buffer is as good as a zeroed one.  At most two buffers are parked (U
   // and V); a request with another layout frees them.  propack_b200_release_cache() empties it.
-  struct BasisLayout { long ld = 0; int cols = 0; int elem = 0; bool operator==(const BasisLayout& o) const { return ld == o.ld && cols == o.cols && elem == o.elem; } };
+  struct BasisLayout {
+    long ld = 0, rows = 0; int cols = 0; int elem = 0;   // rows: the valid rows -- everything below them must be zero
+    bool operator==(const BasisLayout& o) const { return ld == o.ld && rows == o.rows && cols == o.cols && elem == o.elem; }
+  };
   void* basis_acquire(const BasisLayout& lay, bool* zeroed);   // *zeroed = false: fresh allocation, the caller must clear it
   void basis_release(void* p, const BasisLayout& lay);
   void basis_cache_clear();

@@ -326,8 +326,8 @@ template <class T> class Engine {
     hbuf.alloc((size_t)std::max(ucols, vcols) + 8);
     // padding rows must be (and stay) zero: kernels read whole 128-bit packs past the last row.  Recycled basis buffers
     // of the same layout already satisfy that (Context::basis_acquire).
-    ulay.ld = ldu; ulay.cols = ucols; ulay.elem = (int)sizeof(T);
-    vlay.ld = ldv; vlay.cols = vcols; vlay.elem = (int)sizeof(T);
+    ulay.ld = ldu; ulay.rows = m; ulay.cols = ucols; ulay.elem = (int)sizeof(T);
+    vlay.ld = ldv; vlay.rows = n; vlay.cols = vcols; vlay.elem = (int)sizeof(T);
     bool uz = false, vz = false;
     U = static_cast<T*>(c.basis_acquire(ulay, &uz));
     V = static_cast<T*>(c.basis_acquire(vlay, &vz));

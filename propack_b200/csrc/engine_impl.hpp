@@ -389,7 +389,11 @@ int Engine<T>::lansvd_irl(bool smallest, bool jobu, bool jobv, int& dim, int p, 
       // exact shifts with the relative-gap guard doption(4) (:318-344)
       int nshft = 0;
       if (smallest) {
-        for (int i = 0; i < k; ++i) {
+        // The reference fills k = dim-p shifts here (dlansvd_irl.F:320-332) although the p sweeps below consume p of them: for
+        // p > dim/2 the last p-k sweeps run with the zero the workspace was cleared to, which is the documented
+        // "incorrect results if WHICH='S' and P>DIM/2" (Changelog:56).  Filling all p shifts -- the p largest Ritz values,
+        // the ones a smallest-triplet restart must purge -- is identical for p <= dim/2 and correct beyond.
+        for (int i = 0; i < p; ++i) {
           const R ref = th[dim - neig - 1];
           const R relgap = th[i] - wb[i] - ref;
           shift[nshft++] = (relgap > doption[3] * ref) ? th[i] : th[0];

@@ -13,11 +13,17 @@
 //                    - CG columns at a time => S*CG independent LDG.128 in flight per lane
 //                    - CG accumulators folded with a transposing butterfly (CG+2 shuffles, not 5*CG)
 //                    - per-warp column sums accumulate in shared memory, no __syncthreads in the loop
+//   gemv_t_tma_kernel  the same product for long vectors, TMA-staged: one elected producer thread streams 16 KB column
+//                    segments HBM -> shared memory with cp.async.bulk (SASS: UBLKCP) into a 4-stage ring guarded by
+//                    full / empty mbarriers (SYNCS), 8 consumer warps multiply the stage with the CTA's block of q held in
+//                    shared memory; ~64 KB per CTA x 2 CTAs/SM in flight with the register file free
+//                    (tools/gemv_lab.cu measured 7.2-7.3 TB/s against 6.8-7.1 TB/s register-staged)
 //   gemv_t_finalize  h[c] = sum_cta h_part[cta][c]   (fixed order; the hook for the multi-GPU
 //                    all-reduce of the l coefficients)
 //   gemv_n_kernel    out = cin*in -/+ V*h, h staged in shared memory, CU columns unrolled,
 //                    fused ||out||^2 -> last-CTA publication (dreorth's pdnrm2 for free)
 #include <algorithm>
+#include <cstdlib>
 
 #include "comm.hpp"
 #include "kernels.cuh"
@@ -121,6 +127,106 @@ gemv_t_kernel(long L, int l, const T* __restrict__ V, long ldv, const T* __restr
     T s = hs[c];
 #pragma unroll
     for (int ww = 1; ww < 8; ++ww) s = s + hs[ww * GT_CHUNK + c];
+    part[(long)blockIdx.x * lpad + c_begin + c] = s;
+  }
+}
+
+// ---- TMA-staged variant ------------------------------------------------------------------------------------------
+__device__ inline uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ inline void mbar_init(uint64_t* b, int cnt) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(cnt)); }
+__device__ inline void mbar_expect(uint64_t* b, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
+}
+__device__ inline void mbar_arrive(uint64_t* b) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(b)) : "memory"); }
+__device__ inline void mbar_wait(uint64_t* b, uint32_t parity) {
+  asm volatile("{\n.reg .pred p;\nW: mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n@p bra D;\nbra W;\nD:\n}" ::"r"(smem_u32(b)),
+               "r"(parity)
+               : "memory");
+}
+__device__ inline void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* b) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src),
+               "r"(bytes), "r"(smem_u32(b))
+               : "memory");
+}
+
+constexpr int GTT_STAGES = 4;             // ring depth
+constexpr int GTT_STAGE_BYTES = 16384;    // one stage = one column segment of RS = 16 KB / sizeof(T) rows = the CTA's q block
+constexpr int GTT_THREADS = 288;          // 8 consumer warps + 1 producer warp
+template <class T> constexpr int gtt_chunk() { return sizeof(T) <= 8 ? 256 : 128; }   // columns per blockIdx.y slice (hs = 16 KB)
+
+// CTA (bx, by): rows [bx*RC, (bx+1)*RC) in blocks of RS rows, columns [by*chunk, ...).  For every row block the consumers
+// first stage q's block in shared memory, then column after column multiply the 16 KB stage the producer delivered.
+template <class T>
+__global__ void __launch_bounds__(GTT_THREADS)
+gemv_t_tma_kernel(long Lp, int l, const T* __restrict__ V, long ldv, const T* __restrict__ q, T* __restrict__ part, int lpad, int chunk,
+                  long RC) {
+  constexpr int VEC = Pack<T>::N;
+  constexpr int RS = GTT_STAGE_BYTES / (int)sizeof(T);
+  constexpr int S = GTT_STAGES;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  T* stage = reinterpret_cast<T*>(smem_raw);          // [S][RS]
+  T* qs = stage + (size_t)S * RS;                     // [RS]
+  T* hs = qs + RS;                                    // [8][chunk]
+  __shared__ __align__(8) uint64_t full[S], empty[S];
+  const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
+  const int c_begin = blockIdx.y * chunk, c_end = min(l, c_begin + chunk), nc = c_end - c_begin;
+  const long r_lo = (long)blockIdx.x * RC, r_hi = min(Lp, r_lo + RC);
+  const long nrows = r_hi > r_lo ? r_hi - r_lo : 0;   // multiple of VEC (Lp and RC are)
+  const int nblk = (int)((nrows + RS - 1) / RS);
+  if (tid == 0) {
+    for (int s = 0; s < S; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 8); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  for (int i = tid; i < 8 * chunk; i += GTT_THREADS) hs[i] = zero_<T>();
+  __syncthreads();
+  if (w == 8) {
+    // ---- producer: one thread, one bulk copy per (row block, column) --------------------------------------------
+    if (lane == 0) {
+      int st = 0; uint32_t ph = 0;
+      for (int b = 0; b < nblk; ++b) {
+        const long rows = min((long)RS, nrows - (long)b * RS);
+        const T* src = V + (long)c_begin * ldv + r_lo + (long)b * RS;
+        for (int c = 0; c < nc; ++c) {
+          mbar_wait(&empty[st], ph ^ 1);              // slot free (first pass: passes immediately)
+          mbar_expect(&full[st], (uint32_t)(rows * sizeof(T)));
+          bulk_g2s(stage + (size_t)st * RS, src + (long)c * ldv, (uint32_t)(rows * sizeof(T)), &full[st]);
+          if (++st == S) { st = 0; ph ^= 1; }
+        }
+      }
+    }
+    return;
+  }
+  // ---- consumers (warps 0..7) ---------------------------------------------------------------------------------------
+  int st = 0; uint32_t ph = 0;
+  T* hw = hs + w * chunk;
+  for (int b = 0; b < nblk; ++b) {
+    const long rows = min((long)RS, nrows - (long)b * RS);
+    const int npk = (int)(rows / VEC);
+    asm volatile("bar.sync 1, 256;" ::: "memory");   // everybody is done with the previous q block
+    for (int u = tid; u < npk; u += 256) st_pack(qs + (long)u * VEC, ld_pack(q + r_lo + (long)b * RS + (long)u * VEC));
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    for (int c = 0; c < nc; ++c) {
+      mbar_wait(&full[st], ph);
+      const T* sv = stage + (size_t)st * RS;
+      T acc = zero_<T>();
+#pragma unroll 4
+      for (int u = tid; u < npk; u += 256) {
+        const Pack<T> v = ld_pack(sv + (long)u * VEC), qq = ld_pack(qs + (long)u * VEC);
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) fma_conj(acc, v.v[e], qq.v[e]);
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty[st]);
+      if (++st == S) { st = 0; ph ^= 1; }
+      acc = warp_sum(acc);
+      if (lane == 0) hw[c] = hw[c] + acc;
+    }
+  }
+  asm volatile("bar.sync 1, 256;" ::: "memory");
+  for (int c = tid; c < nc; c += 256) {
+    T s = hs[c];
+#pragma unroll
+    for (int ww = 1; ww < 8; ++ww) s = s + hs[ww * chunk + c];
     part[(long)blockIdx.x * lpad + c_begin + c] = s;
   }
 }
@@ -286,6 +392,14 @@ gemv_n_kernel(long L, int l, const T* __restrict__ V, long ldv, const T* __restr
 
 }  // namespace
 
+// The TMA-staged kernel pays off once every CTA streams many 16 KB stages (long vectors, a few columns at least);
+// PROPACK_B200_GEMV_TMA=0 / 1 forces the choice.
+inline bool gemv_t_use_tma(long L, int l) {
+  static const int forced = [] { const char* e = std::getenv("PROPACK_B200_GEMV_TMA"); return e ? (e[0] == '0' ? 0 : 1) : -1; }();
+  if (forced >= 0) return forced == 1;
+  return L >= 262144 && l >= 8;
+}
+
 template <class T> void k_gemv_t(Context& c, long L, int l, const T* V, long ldv, const T* q, T* h) {
   if (l <= 0) return;
   constexpr int VEC = Pack<T>::N;
@@ -296,15 +410,35 @@ template <class T> void k_gemv_t(Context& c, long L, int l, const T* V, long ldv
   int gx = (int)std::min<long>(ceil_div(L, wrows * 8), std::max(1, (2 * c.num_sms) / nchunks));
   if (gx < 1) gx = 1;
   const int lpad = (l + 3) / 4 * 4;
-  T* part = static_cast<T*>(c.scratch(sizeof(T) * (size_t)gx * lpad));
-  const size_t smem = sizeof(T) * 8 * GT_CHUNK;
-  static bool attr_set = false;
-  if (!attr_set) {
-    PB_CUDA(cudaFuncSetAttribute(gemv_t_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
+  T* part;
+  if (gemv_t_use_tma(L, l)) {
+    // TMA-staged: 2 CTAs per SM over (row ranges) x (column slices); a CTA's rows are a multiple of the pack size
+    const int tchunks = ceil_div(l, gtt_chunk<T>());
+    const int tchunk = ceil_div(l, tchunks);
+    const long Lp = (L + VEC - 1) / VEC * VEC;
+    gx = std::max(1, (2 * c.num_sms) / tchunks);
+    const long RC = (ceil_div(Lp, gx) + 31) / 32 * 32;
+    gx = ceil_div(Lp, RC);
+    part = static_cast<T*>(c.scratch(sizeof(T) * (size_t)gx * lpad));
+    const size_t smem = (size_t)GTT_STAGES * GTT_STAGE_BYTES + GTT_STAGE_BYTES + sizeof(T) * 8 * (size_t)gtt_chunk<T>() + 128;
+    static bool tma_attr_set = false;
+    if (!tma_attr_set) {
+      PB_CUDA(cudaFuncSetAttribute(gemv_t_tma_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      tma_attr_set = true;
+    }
+    gemv_t_tma_kernel<T><<<dim3(gx, tchunks), GTT_THREADS, smem, c.stream>>>(Lp, l, V, ldv, q, part, lpad, tchunk, RC);
+    PB_LAUNCH_CHECK();
+  } else {
+    part = static_cast<T*>(c.scratch(sizeof(T) * (size_t)gx * lpad));
+    const size_t smem = sizeof(T) * 8 * GT_CHUNK;
+    static bool attr_set = false;
+    if (!attr_set) {
+      PB_CUDA(cudaFuncSetAttribute(gemv_t_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      attr_set = true;
+    }
+    gemv_t_kernel<T><<<dim3(gx, nchunks), kThreads, smem, c.stream>>>(L, l, V, ldv, q, part, lpad, chunk);
+    PB_LAUNCH_CHECK();
   }
-  gemv_t_kernel<T><<<dim3(gx, nchunks), kThreads, smem, c.stream>>>(L, l, V, ldv, q, part, lpad, chunk);
-  PB_LAUNCH_CHECK();
   if (c.dist_reduce && c.coef_table != nullptr && l <= Comm::kCoefMax) {
     // fused: finalize + cross-rank all-reduce of the coefficients over NVLink peer memory, one launch
     c.coef_seq += 1;

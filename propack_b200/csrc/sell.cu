@@ -188,11 +188,12 @@ spmv_sell_kernel(SellDevice<T> S, const T* __restrict__ x, T* y, real_t<T> coef,
 
 // kernel variant: PROPACK_B200_SELL_VARIANT = 0 (U = 8, 5 CTAs/SM), 1 (U = 8, 4 CTAs/SM: no register cap; the default -- measured
 // best on configs 2 and 5: 32 warps x 8 gather chains beat more warps with spills or shorter batches), 2 (U = 4, 8 CTAs/SM),
-// 3 (U = 12, 3 CTAs/SM), 4 (U = 16, 2 CTAs/SM)
+// 3 (U = 12, 3 CTAs/SM), 4 (U = 16, 2 CTAs/SM).  Measured (us, configs 5 / 2 / 4, A x and A^H x): variant 1: 534 588 / 68 68 / 272 136;
+// variant 0: 621 652 / 74 73; variant 2: 778 798 / 88 89 / 394 209; variant 3: 570 587 / 71 72 / 306 154; variant 4: 771 793 / 79 78 / 416 243.
 template <class T> int sell_variant() {
   static const int v = [] {
     const char* e = std::getenv("PROPACK_B200_SELL_VARIANT");
-    const int d = sizeof(T) <= 8 ? 1 : 2;
+    const int d = 1;
     const int u = e ? std::atoi(e) : d;
     return (u < 0 || u > 4) ? d : u;
   }();

@@ -31,10 +31,16 @@ def _r(pfx, v):
     return C.byref((C.c_float if REAL[pfx] is np.float32 else C.c_double)(v))
 
 
+def _is_torch_tensor(A):
+    mod = type(A).__module__
+    return mod == "torch" or mod.startswith("torch.")
+
+
 class Operator:
     """A linear operator the drivers can use.
 
     * scipy sparse matrix / dense ndarray -> registered on the device (built-in APROD, handle in IPARM(1));
+    * torch tensor (dense or sparse CSR; a CUDA tensor never leaves the device) or any object with ``__dlpack__`` -> same;
     * anything with ``matvec``/``rmatvec`` (a LinearOperator) -> Python APROD callback with the reference's
       contract (dlansvd.F:20-33), host-staged.
     """
@@ -58,6 +64,8 @@ class Operator:
             self.handle = check(getattr(L, f"propack_b200_csr_create_{self.pfx}")(
                 C.c_int(A.shape[0]), C.c_int(A.shape[1]), _p(rp), _p(ci), _p(va), C.c_int(0)), "csr_create")
             self.nnz = int(A.nnz)
+        elif _is_torch_tensor(A):
+            self._init_from_torch(A, dtype)
         elif isinstance(A, np.ndarray):
             dtype = np.dtype(dtype or A.dtype)
             if dtype not in PREFIX:
@@ -66,6 +74,9 @@ class Operator:
             self.dtype, self.pfx, self.shape = dtype, PREFIX[dtype], Af.shape
             self.handle = check(getattr(L, f"propack_b200_dense_create_{self.pfx}")(
                 C.c_int(Af.shape[0]), C.c_int(Af.shape[1]), _p(Af), C.c_long(Af.shape[0])), "dense_create")
+        elif hasattr(A, "__dlpack__") and not hasattr(A, "matvec"):
+            import torch
+            self._init_from_torch(torch.from_dlpack(A), dtype)
         else:  # LinearOperator-like
             dtype = np.dtype(dtype or getattr(A, "dtype", np.float64))
             if dtype not in PREFIX:
@@ -86,6 +97,41 @@ class Operator:
             self._cb = self._cbtype(cb)
         self.iparm = np.array([self.handle, 0], dtype=np.int32)
         self.parm = np.zeros(2, dtype=self.dtype)
+
+    def _init_from_torch(self, A, dtype):
+        """A torch tensor (or anything exposing ``__dlpack__`` was converted to one): a CUDA tensor stays on the device -- a dense one
+        is laid out column-major with zeroed padding rows by a device-to-device copy and adopted without passing through the
+        host; a sparse CSR one hands its device arrays to ``csr_create`` (cudaMemcpyDefault).  CPU tensors go through numpy."""
+        import torch
+        L = lib()
+        tmap = {torch.float32: np.float32, torch.float64: np.float64, torch.complex64: np.complex64, torch.complex128: np.complex128}
+        if A.layout == torch.sparse_csr:
+            npdt = np.dtype(dtype or tmap.get(A.dtype, np.float64))
+            tdt = {v: k for k, v in tmap.items()}[npdt.type]
+            crow = A.crow_indices().to(torch.int32).contiguous()
+            col = A.col_indices().to(torch.int32).contiguous()
+            val = A.values().to(tdt).contiguous()
+            self.dtype, self.pfx, self.shape = npdt, PREFIX[npdt], tuple(A.shape)
+            self.handle = check(getattr(L, f"propack_b200_csr_create_{self.pfx}")(
+                C.c_int(A.shape[0]), C.c_int(A.shape[1]), C.c_void_p(crow.data_ptr()), C.c_void_p(col.data_ptr()),
+                C.c_void_p(val.data_ptr()), C.c_int(0)), "csr_create")
+            if A.is_cuda:
+                torch.cuda.synchronize()
+            self.nnz = int(val.numel())
+            return
+        if not A.is_cuda:
+            return self.__init__(A.detach().cpu().numpy(), dtype)
+        npdt = np.dtype(dtype or tmap.get(A.dtype, np.float64))
+        tdt = {v: k for k, v in tmap.items()}[npdt.type]
+        m, n = A.shape
+        ld = (m + 31) // 32 * 32
+        buf = torch.zeros((n, ld), dtype=tdt, device=A.device)       # row j of buf = column j of A: column-major, lda = ld
+        buf[:, :m] = A.detach().to(tdt).t()
+        torch.cuda.synchronize(A.device)
+        self._device_store = buf                                      # adopted, not copied: keep it alive
+        self.dtype, self.pfx, self.shape = npdt, PREFIX[npdt], (m, n)
+        self.handle = check(getattr(L, f"propack_b200_dense_adopt_device_{self.pfx}")(
+            C.c_int(m), C.c_int(n), C.c_void_p(buf.data_ptr()), C.c_long(ld)), "dense_adopt_device")
 
     @property
     def aprod(self):

@@ -82,3 +82,24 @@ def svdp(A, k, which="LM", irl_mode=True, kmax=None, compute_u=True, compute_v=T
     finally:
         if owns:
             op.close()
+
+
+def svds(A, k=6, ncv=None, tol=0, which="LM", v0=None, maxiter=None, return_singular_vectors=True, solver="propack", rng=None,
+         options=None):
+    """``scipy.sparse.linalg.svds(..., solver='propack')`` on this library: same arguments, defaults and return convention
+    (singular values in ASCENDING order, ``u, s, vh``; ``return_singular_vectors`` in {True, False, "u", "vh"}).  SciPy's svds maps
+    ``maxiter`` to PROPACK's ``kmax`` and always uses the implicitly restarted driver; so does this."""
+    if solver != "propack":
+        raise ValueError("propack_b200.svds only implements solver='propack'")
+    if which not in {"LM", "SM"}:
+        raise ValueError("`which` must be either 'LM' or 'SM'.")
+    if return_singular_vectors not in {True, False, "u", "vh"}:
+        raise ValueError("`return_singular_vectors` must be in {True, False, 'u', 'vh'}.")
+    jobu = return_singular_vectors in {True, "u"}
+    jobv = return_singular_vectors in {True, "vh"}
+    u, s, vh, _ = svdp(A, k=k, tol=tol, which=which, maxiter=None, compute_u=jobu, compute_v=jobv, irl_mode=True, kmax=maxiter, v0=v0,
+                       rng=rng)
+    u, s, vh = u[:, ::-1], s[::-1], vh[::-1]
+    if not return_singular_vectors:
+        return s
+    return (u if jobu else None), s, (vh if jobv else None)

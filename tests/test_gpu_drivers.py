@@ -163,6 +163,25 @@ def test_smallest_triplets_irl(oracle):
     op.close()
 
 
+@pytest.mark.parametrize("dim,p", [(30, 20), (24, 18), (40, 10)])
+def test_smallest_triplets_irl_many_shifts(dim, p):
+    """which='S' with p > dim/2 -- the case the reference documents as broken (Changelog:56, dlansvd_irl.F:318-332: only dim-p
+    shifts are filled for p sweeps) -- and p < dim/2, against dense LAPACK SVD (the oracle reproduces the reference's defect)."""
+    from propack_b200 import f77
+    rng = np.random.default_rng(4)
+    Q1, _ = np.linalg.qr(rng.standard_normal((120, 60)))
+    Q2, _ = np.linalg.qr(rng.standard_normal((60, 60)))
+    s = np.linspace(1.0, 4.0, 60)
+    A = (Q1 * s) @ Q2.T
+    op = f77.Operator(A)
+    got = f77.lansvd_irl(op, 3, dim, p=p, which="S", tol=1e-10, u0=rng.uniform(size=120), maxiter=2000)
+    op.close()
+    assert got["info"] == 0 and got["k"] == 3
+    assert relerr(np.sort(got["sigma"]), np.sort(s)[:3]) < 1e-8
+    U, S, V = got["U"], got["sigma"], got["V"]
+    assert np.max(np.linalg.norm(A @ V - U * S, axis=0)) < 1e-7
+
+
 def test_thin_hilbert_and_fat_random(oracle):
     """SciPy test_thin_hilbert (200x4, k=4: j == min(m,n), dbdqr ignorelast) and test_fat_random (3x100, k=3)."""
     from propack_b200 import f77
@@ -372,3 +391,68 @@ def test_example_driver_on_illc1850_rra():
                         "--kmax", "100", "--compare", os.path.join(GOLDEN, "Sigma_illc1850.ascii")], capture_output=True, text=True, timeout=600)
     sys.stdout.write(p.stdout[-3000:]); sys.stderr.write(p.stderr[-2000:])
     assert p.returncode == 0 and "max relative error of sigma" in p.stdout
+
+
+@pytest.mark.gpu
+def test_example_programs_all_formats(tmp_path):
+    """The rest of the reference's Examples layer (README:89-121): example_irl on illc1850.rra, the complex example on
+    mhd1280b.cua, and example.py on coordinate / binary-dense / diagonal files, each checked against stored singular values."""
+    import importlib.util
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("make_example_data", os.path.join(root, "examples", "make_example_data.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    data = mod.main(os.path.join(tmp_path, "data"))
+    ex, ex_irl = os.path.join(root, "examples", "example.py"), os.path.join(root, "examples", "example_irl.py")
+    sig_real = os.path.join(GOLDEN, "Sigma_illc1850.ascii")
+    runs = [
+        [ex_irl, os.path.join(GOLDEN, "illc1850.rra"), "--k", "10", "--kmax", "50", "--p", "40", "--compare", sig_real],
+        [ex, os.path.join(data, "mhd1280b.cua"), "--k", "10", "--kmax", "200", "--compare", os.path.join(data, "Sigma_mhd1280b.ascii")],
+        [ex_irl, os.path.join(data, "mhd1280b.cua"), "--k", "6", "--kmax", "40", "--p", "20", "--compare", os.path.join(data, "Sigma_mhd1280b.ascii")],
+        [ex, os.path.join(data, "illc1850.coord"), "--k", "10", "--kmax", "100", "--compare", sig_real],
+        [ex, os.path.join(data, "illc1850.cbin"), "--k", "10", "--kmax", "100", "--precision", "single", "--tol", "1e-6", "--compare", sig_real],
+        [ex, os.path.join(data, "illc1850.bin"), "--k", "10", "--kmax", "100", "--compare", sig_real],
+        [ex, os.path.join(data, "band4000.diag"), "--k", "5", "--kmax", "400"],
+    ]
+    for cmd in runs:
+        p = subprocess.run([sys.executable] + cmd, capture_output=True, text=True, timeout=600)
+        sys.stdout.write(p.stdout[-1500:]); sys.stderr.write(p.stderr[-1500:])
+        assert p.returncode == 0, cmd
+        if "--compare" in cmd:
+            assert "max relative error of sigma" in p.stdout
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype", [np.float64, np.complex128, np.float32])
+def test_svdp_accepts_torch_device_arrays(dtype):
+    """svdp / svds on arrays that already live on the GPU (torch CUDA tensors, dense and sparse CSR, and DLPack exporters): the
+    operator is built by device-to-device copies, and the answer matches dense LAPACK SVD."""
+    import torch
+    from propack_b200 import svdp, svds
+    rng = np.random.default_rng(2)
+    A = rng.standard_normal((301, 77)) @ np.diag(np.linspace(1, 3, 77))
+    if np.issubdtype(dtype, np.complexfloating):
+        A = A + 1j * rng.standard_normal(A.shape)
+    A = A.astype(dtype)
+    want = np.linalg.svd(A.astype(np.complex128 if np.iscomplexobj(A) else np.float64), compute_uv=False)
+    tol = TOL[dtype]
+    At = torch.from_numpy(A).cuda()
+    u, s, vh, _ = svdp(At, 5, irl_mode=False, kmax=60, rng=np.random.default_rng(0))
+    assert relerr(s, want[:5]) < tol
+    assert np.linalg.norm(A @ vh.conj().T - u * s) < (1e-4 if dtype == np.float32 else 1e-9) * s[0] * 10
+    Asp = sp.csr_array(np.where(np.abs(A) > 1.0, A, 0))
+    wsp = np.linalg.svd(Asp.toarray().astype(np.complex128 if np.iscomplexobj(A) else np.float64), compute_uv=False)
+    Tsp = torch.sparse_csr_tensor(torch.from_numpy(Asp.indptr.astype(np.int64)), torch.from_numpy(Asp.indices.astype(np.int64)),
+                                  torch.from_numpy(Asp.data), size=Asp.shape).cuda()
+    u, s, vh, _ = svdp(Tsp, 4, irl_mode=True, kmax=40, rng=np.random.default_rng(0))
+    assert relerr(s, wsp[:4]) < tol
+
+    class Exporter:                      # anything with __dlpack__ (cupy / jax / ... arrays)
+        def __init__(self, t): self.t = t
+        def __dlpack__(self, **kw): return self.t.__dlpack__(**kw)
+        def __dlpack_device__(self): return self.t.__dlpack_device__()
+    uu, ss, vv = svds(Exporter(At), k=3, maxiter=40, rng=np.random.default_rng(0))
+    assert relerr(ss[::-1], want[:3]) < tol and np.all(np.diff(ss) >= 0)      # scipy's svds returns ascending order
+    assert svds(At, k=2, return_singular_vectors=False, maxiter=30, rng=np.random.default_rng(0)).shape == (2,)

@@ -118,6 +118,25 @@ def test_reorth_matches_oracle(oracle, dtype, n, k, index, iflag):
         assert np.max(np.abs(V[:, sel].conj().T @ got)) < 50 * eps * max(gn, 1.0) * np.sqrt(n)
 
 
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("n,k,index", [
+    (300_001, 37, [1, 37, 38]),               # long vectors: the TMA-staged GEMV^T (cp.async.bulk ring), odd row count
+    (524_288, 300, [2, 150, 160, 299, 301]),  # > 256 columns: two column slices per row range; two intervals
+])
+def test_reorth_long_vectors_tma_path(oracle, dtype, n, k, index):
+    """dreorth_ on vectors long enough for the TMA-staged kernel (L >= 262144), against the oracle."""
+    from propack_b200 import f77
+    rng = np.random.default_rng(k)
+    V = np.asfortranarray(rand_vec(rng, n * k, dtype).reshape(n, k) / np.sqrt(n)).astype(dtype)
+    v = rand_vec(rng, n, dtype)
+    nrm0 = float(np.linalg.norm(v))
+    got, gn = f77.reorth(V, v, nrm0, index, 0.717, 1)
+    want, wn = oracle.reorth(V, v, nrm0, index, 0.717, 1)
+    tol = TOL[dtype]
+    assert abs(gn - wn) <= tol * wn
+    assert rel(got, want) < tol
+
+
 @pytest.mark.parametrize("dtype", [np.float64, np.complex128])
 def test_reorth_vector_in_span_is_zeroed(oracle, dtype):
     """dreorth.F:85-98: a vector that keeps failing the DGKS test for NTRY passes is zeroed.  With V = unit
