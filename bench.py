@@ -587,7 +587,10 @@ def run_ours_sharded(args):
     A, u0, k, kmax, tol = make_matrix(args.workload)     # every rank builds the same seeded matrix, keeps its shard
     m, n = A.shape
     lanmax = min(m + 1, n + 1, kmax)
-    op = pdist.ShardedOperator(A, rank, world)
+    dense = isinstance(A, DenseSpec)
+    make_sharded = ((lambda: pdist.ShardedDenseOperator((m, n), rank, world, synthetic=(DENSE_SEED, A.table))) if dense else
+                    (lambda: pdist.ShardedOperator(A, rank, world)))
+    op = make_sharded()
     sv = pdist.Solver(op, lanmax + 1, lanmax)
 
     def barrier():
@@ -627,20 +630,26 @@ def run_ours_sharded(args):
     propack_b200.set_profile(False)
 
     # e2e: this rank's shard from pinned host memory -> device, solve, its slices of U, V and sigma back to the host
-    rows, colt = pdist.shard_csr(A, world, rank)
     pin = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a, dtype=dt)).pin_memory().numpy()
-    harr = (pin(rows.indptr, np.int32), pin(rows.indices, np.int32), pin(rows.data, np.float64),
-            pin(colt.indptr, np.int32), pin(colt.indices, np.int32), pin(colt.data, np.float64))
+    if dense:   # the operator has no host copy: e2e = generate this rank's rows on the device + solve + result slices to the host
+        harr = ()
+    else:
+        rows, colt = pdist.shard_csr(A, world, rank)
+        harr = (pin(rows.indptr, np.int32), pin(rows.indices, np.int32), pin(rows.data, np.float64),
+                pin(colt.indptr, np.int32), pin(colt.indices, np.int32), pin(colt.data, np.float64))
     sv.close(); op.close()
     e2e_t, e2e_steps = [], 0
     for i in range(0 if args.no_e2e else 1 + max(1, min(args.steps, 3))):
         barrier()
         t0 = time.perf_counter()
-        h = _lib.check(L.propack_b200_csr_create_sharded_d(C.c_int(m), C.c_int(n), *[a.ctypes.data_as(C.c_void_p) for a in harr], C.c_int(0)),
-                       "csr_create_sharded")
-        op2 = pdist.ShardedOperator.__new__(pdist.ShardedOperator)
-        op2.handle, op2.dtype, op2.pfx, op2.shape, op2.rank, op2.world = h, np.dtype(np.float64), "d", (m, n), rank, world
-        op2.rows, op2.cols = pdist.shard_bounds(m, world, rank), pdist.shard_bounds(n, world, rank)
+        if dense:
+            op2 = make_sharded()
+        else:
+            h = _lib.check(L.propack_b200_csr_create_sharded_d(C.c_int(m), C.c_int(n), *[a.ctypes.data_as(C.c_void_p) for a in harr], C.c_int(0)),
+                           "csr_create_sharded")
+            op2 = pdist.ShardedOperator.__new__(pdist.ShardedOperator)
+            op2.handle, op2.dtype, op2.pfx, op2.shape, op2.rank, op2.world = h, np.dtype(np.float64), "d", (m, n), rank, world
+            op2.rows, op2.cols = pdist.shard_bounds(m, world, rank), pdist.shard_bounds(n, world, rank)
         sv2 = pdist.Solver(op2, lanmax + 1, lanmax)
         sv2.set_start(u0)
         propack_b200.reset_counters()
@@ -657,7 +666,7 @@ def run_ours_sharded(args):
     te = torch.tensor([float(np.sum(e2e_t)) if e2e_t else 1.0], device="cuda"); dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_val = e2e_steps / float(te.item())
     rows_b, cols_b = pdist.shard_bounds(m, world, rank), pdist.shard_bounds(n, world, rank)
-    h2d = sum(a.nbytes for a in harr) + (rows_b[1] - rows_b[0]) * 8
+    h2d = sum(a.nbytes for a in harr) + (rows_b[1] - rows_b[0]) * 8 + (A.table.nbytes if dense else 0)
     d2h = ((rows_b[1] - rows_b[0]) + (cols_b[1] - cols_b[0])) * k * 8 + 2 * k * 8
     nar, nag, agb = C.c_longlong(0), C.c_longlong(0), C.c_double(0)
     L.propack_b200_comm_stats(C.byref(nar), C.byref(nag), C.byref(agb))

@@ -317,6 +317,16 @@ int propack_b200_csr_create_sharded_c(int m_global, int n_global, const int* row
                                       const int* colt_rowptr, const int* colt_rowind, const pb200_complex8* colt_values, int index_base);
 int propack_b200_csr_create_sharded_z(int m_global, int n_global, const int* row_rowptr, const int* row_colind, const pb200_complex16* row_values,
                                       const int* colt_rowptr, const int* colt_rowind, const pb200_complex16* colt_values, int index_base);
+/* Row-sharded DENSE operator of THIS rank (BASELINE configs[2] on N GPUs): A_rows = A[r0:r1, :] column-major with leading
+ * dimension lda (host or device memory), [r0,r1) from _shard_bounds(m_global).  A x = all-gather of the n-vector + local GEMV;
+ * A^H u = local GEMV^T + all-reduce of the n coefficients, every rank keeping its slice.  Replaces the user's APROD
+ * (double/dlansvd.F:20-33) the way the reference's OpenMP build chunks rows (double/dreorth.F:147-208). */
+int propack_b200_dense_create_sharded_s(int m_global, int n_global, const float* A_rows, long lda);
+int propack_b200_dense_create_sharded_d(int m_global, int n_global, const double* A_rows, long lda);
+int propack_b200_dense_create_sharded_c(int m_global, int n_global, const pb200_complex8* A_rows, long lda);
+int propack_b200_dense_create_sharded_z(int m_global, int n_global, const pb200_complex16* A_rows, long lda);
+/* this rank's rows of the synthetic dense matrix of _dense_create_synthetic_d (same matrix, evaluated on the device) */
+int propack_b200_dense_create_synthetic_sharded_d(int m_global, int n_global, unsigned long long seed, const double* table16x256);
 /* local slice sizes of a solver session (U is m_local x ucols with leading dimension ldu on the device, ...) */
 int propack_b200_solver_local_rows(int solver, int* m_local, int* n_local, long* ldu, long* ldv);
 

@@ -46,7 +46,7 @@ template <> struct abi<cplx<double>> { using type = pb200_complex16; static cons
 
 struct OpEntry {
   char tag = 0;
-  int kind = 0;  // 0 csr, 1 dense, 2 row-sharded csr
+  int kind = 0;  // 0 csr, 1 dense, 2 row-sharded csr, 3 row-sharded dense
   std::shared_ptr<void> op;
 };
 struct SolverEntry {
@@ -175,6 +175,39 @@ int csr_create_sharded(int mg, int ng, const int* row_rp, const int* row_ci, con
   upload(1, nl, mg, op->ld_m, colt_rp, colt_ci, colt_va);
   op->alloc_gather_buffers();
   OpEntry e; e.tag = abi<T>::tag; e.kind = 2; e.op = op;
+  return register_op(e);
+  PB_API_CATCH(return code__)
+}
+
+// Row-sharded dense operator (BASELINE config 3 on N GPUs): `A_rows` = this rank's row block A[r0:r1, :]
+// (column-major, leading dimension lda >= r1-r0; host or device memory), bounds from shard_bounds().
+template <class T> std::shared_ptr<ShardedDenseOperator<T>> sharded_dense_shell(int mg, int ng) {
+  Comm& cm = Comm::get();
+  if (mg <= 0 || ng <= 0) throw std::runtime_error("propack_b200: bad sharded dense arguments");
+  long r0, r1, c0, c1;
+  shard_bounds(mg, cm.world, cm.rank, r0, r1);
+  shard_bounds(ng, cm.world, cm.rank, c0, c1);
+  auto op = std::make_shared<ShardedDenseOperator<T>>();
+  op->m = (int)(r1 - r0); op->n = (int)(c1 - c0); op->mg = mg; op->ng = ng; op->m_off = r0; op->n_off = c0;
+  op->ld_m = shard_slice(mg, cm.world); op->ld_n = shard_slice(ng, cm.world);
+  op->sharded = true;
+  const long ld = Engine<T>::pad_ld(std::max(op->m, 1));
+  op->store.alloc((size_t)ld * ng);
+  PB_CUDA(cudaMemsetAsync(op->store.p, 0, sizeof(T) * (size_t)ld * ng, Context::get().stream));   // zero padding rows
+  op->A = op->store.p; op->lda = ld;
+  op->alloc_buffers();
+  return op;
+}
+template <class T> int dense_create_sharded(int mg, int ng, const void* A_rows, long lda) {
+  PB_API_TRY
+  Context& c = Context::get();
+  auto op = sharded_dense_shell<T>(mg, ng);
+  if (op->m > 0) {
+    if (!A_rows || lda < op->m) throw std::runtime_error("propack_b200: bad sharded dense row block");
+    PB_CUDA(cudaMemcpy2DAsync(op->store.p, sizeof(T) * op->lda, A_rows, sizeof(T) * lda, sizeof(T) * op->m, ng, cudaMemcpyDefault, c.stream));
+  }
+  c.sync();
+  OpEntry e; e.tag = abi<T>::tag; e.kind = 3; e.op = op;
   return register_op(e);
   PB_API_CATCH(return code__)
 }
@@ -835,6 +868,29 @@ int propack_b200_dense_create_synthetic_d(int m, int n, unsigned long long seed,
   k_dense_synth(c, m, n, ld, seed, table16x256, op->store.p);
   op->A = op->store.p; op->lda = ld;
   OpEntry e; e.tag = 'd'; e.kind = 1; e.op = op;
+  return register_op(e);
+  PB_API_CATCH(return code__)
+}
+int propack_b200_dense_create_sharded_s(int m_global, int n_global, const float* A_rows, long lda) {
+  return dense_create_sharded<float>(m_global, n_global, A_rows, lda);
+}
+int propack_b200_dense_create_sharded_d(int m_global, int n_global, const double* A_rows, long lda) {
+  return dense_create_sharded<double>(m_global, n_global, A_rows, lda);
+}
+int propack_b200_dense_create_sharded_c(int m_global, int n_global, const pb200_complex8* A_rows, long lda) {
+  return dense_create_sharded<cplx<float>>(m_global, n_global, A_rows, lda);
+}
+int propack_b200_dense_create_sharded_z(int m_global, int n_global, const pb200_complex16* A_rows, long lda) {
+  return dense_create_sharded<cplx<double>>(m_global, n_global, A_rows, lda);
+}
+// this rank's rows of the synthetic config-3 matrix, evaluated on the device (the same matrix as the 1-GPU generator)
+int propack_b200_dense_create_synthetic_sharded_d(int m_global, int n_global, unsigned long long seed, const double* table16x256) {
+  PB_API_TRY
+  Context& c = Context::get();
+  if (!table16x256) throw std::runtime_error("propack_b200: bad synthetic dense arguments");
+  auto op = sharded_dense_shell<double>(m_global, n_global);
+  k_dense_synth(c, op->m, n_global, op->lda, seed, table16x256, op->store.p, op->m_off);
+  OpEntry e; e.tag = 'd'; e.kind = 3; e.op = op;
   return register_op(e);
   PB_API_CATCH(return code__)
 }

@@ -23,14 +23,16 @@ __host__ __device__ inline unsigned long long splitmix64(unsigned long long z) {
 }
 
 __global__ void __launch_bounds__(256)
-dense_synth_kernel(long m, int n, long lda, unsigned long long seed, const double* __restrict__ table, double* __restrict__ A) {
+dense_synth_kernel(long m, int n, long lda, unsigned long long seed, const double* __restrict__ table, double* __restrict__ A, long row0) {
   __shared__ double T[16 * 256];
   for (int i = threadIdx.x; i < 16 * 256; i += 256) T[i] = table[i];
   __syncthreads();
   // a CTA owns a strip of 256 consecutive rows (coalesced column-major stores) and sweeps a slab of columns
-  const long i = (long)blockIdx.x * 256 + threadIdx.x;
+  // (row0 = global index of local row 0: a row-sharded operator evaluates only its own rows of the same matrix)
+  const long il = (long)blockIdx.x * 256 + threadIdx.x;
   const int j0 = blockIdx.y * 64, j1 = min(n, j0 + 64);
-  if (i >= m) return;
+  if (il >= m) return;
+  const long i = row0 + il;
   const unsigned long long x0 = splitmix64(seed ^ (0x1000000000000000ull + 2ull * (unsigned long long)i));
   const unsigned long long x1 = splitmix64(seed ^ (0x1000000000000000ull + 2ull * (unsigned long long)i + 1ull));
   for (int j = j0; j < j1; ++j) {
@@ -44,17 +46,18 @@ dense_synth_kernel(long m, int n, long lda, unsigned long long seed, const doubl
     w = x1 ^ y1;
 #pragma unroll
     for (int g = 0; g < 8; ++g) a = __dadd_rn(a, T[(8 + g) * 256 + (int)((w >> (8 * g)) & 255ull)]);
-    A[(long)j * lda + i] = a;
+    A[(long)j * lda + il] = a;
   }
 }
 
 }  // namespace
 
-void k_dense_synth(Context& c, long m, int n, long lda, unsigned long long seed, const double* table_host, double* A) {
+void k_dense_synth(Context& c, long m, int n, long lda, unsigned long long seed, const double* table_host, double* A, long row0) {
   DeviceBuffer<double> tab(16 * 256);
   PB_CUDA(cudaMemcpyAsync(tab.p, table_host, sizeof(double) * 16 * 256, cudaMemcpyHostToDevice, c.stream));
+  if (m <= 0) { c.sync(); return; }
   dim3 grid((unsigned)((m + 255) / 256), (unsigned)((n + 63) / 64));
-  dense_synth_kernel<<<grid, 256, 0, c.stream>>>(m, n, lda, seed, tab.p, A);
+  dense_synth_kernel<<<grid, 256, 0, c.stream>>>(m, n, lda, seed, tab.p, A, row0);
   PB_LAUNCH_CHECK();
   c.sync();
 }

@@ -277,6 +277,45 @@ template <class T> struct DenseOperator : LinOp<T> {
   Pending scratch_p{};
 };
 
+// Row-sharded dense operator (BASELINE config 3 on N GPUs): this rank holds the rows [m_off, m_off+m) of A
+// (column-major, all ng columns).  V-vectors are block-sharded like everywhere else, so
+//   A x   : all-gather the n-vector (ng*w bytes -- tiny next to the m_loc x ng block), then the local GEMV;
+//   A^H u : local GEMV^T gives this rank's contribution to all ng coefficients, all-reduce of those ng values
+//           (the north star's "allreduce of length-k coefficients" pattern), then every rank keeps its own slice.
+// The products themselves are the reorthogonalisation GEMV kernels over A, as on one GPU (DenseOperator).
+template <class T> struct ShardedDenseOperator : LinOp<T> {
+  using R = real_t<T>;
+  DeviceBuffer<T> store, xfull, tfull;
+  const T* A = nullptr; long lda = 0;
+  void alloc_buffers() {
+    xfull.alloc((size_t)this->ld_n * Comm::get().world);
+    tfull.alloc((size_t)this->ld_n * Comm::get().world);
+    PB_CUDA(cudaMemset(xfull.p, 0, sizeof(T) * xfull.n));
+    PB_CUDA(cudaMemset(tfull.p, 0, sizeof(T) * tfull.n));
+  }
+  void apply(Context& c, bool adjoint, const T* x, T* y, R coef, const T* prev, Pending* nrm) override {
+    Comm& cm = Comm::get();
+    if (!adjoint) {
+      // slices are ld_n long and contiguous in the global index, so the gathered buffer is the global vector
+      cm.allgather(x, xfull.p, sizeof(T) * (size_t)this->ld_n, c.stream);
+      k_gemv_n<T>(c, this->m, this->ng, A, lda, xfull.p, coef, prev, +1, y, nrm);
+    } else {
+      {  // local contribution only: the cross-rank sum is the explicit all-reduce below, whatever the engine's mode
+        const bool old = c.dist_reduce; c.dist_reduce = false;
+        k_gemv_t<T>(c, this->m, this->ng, A, lda, x, tfull.p);
+        c.dist_reduce = old;
+      }
+      cm.allreduce_sum(reinterpret_cast<R*>(tfull.p), (size_t)this->ng * (scalar_traits<T>::is_complex ? 2 : 1), c.stream);
+      if (this->n > 0)
+        PB_CUDA(cudaMemcpyAsync(y, tfull.p + this->n_off, sizeof(T) * (size_t)this->n, cudaMemcpyDeviceToDevice, c.stream));
+      if (prev) k_axpy_nrm<T>(c, this->n, T(coef), prev, y, nrm ? nrm : &scratch_p);
+      else if (nrm) k_nrm2<T>(c, this->n, y, nrm);
+    }
+  }
+  double algorithmic_bytes(bool) const override { return (double)this->m * this->ng * sizeof(T); }
+  Pending scratch_p{};
+};
+
 // Generic user callback: host-staged (D2H x, call, H2D y).  Correct, PCIe-bound; the fast path is a
 // built-in operator handle.
 template <class T> struct CallbackOperator : LinOp<T> {

@@ -120,7 +120,7 @@ int k_csr_split_phases(Context& c, int rows, long width, const int* rp, const in
                        int* const* out_rp, DeviceBuffer<int>* const* out_ci, DeviceBuffer<T>* const* out_va, long* nnz_out);
 
 // synthetic dense operator A(i,j) = u(i,j) + planted rank-128 part, evaluated on the device (dense_gen.cu)
-void k_dense_synth(Context& c, long m, int n, long lda, unsigned long long seed, const double* table_host, double* A);
+void k_dense_synth(Context& c, long m, int n, long lda, unsigned long long seed, const double* table_host, double* A, long row0 = 0);
 
 // --- tall in-place GEMM (reference: dgemm_ovwr_left, double/dgemm_ovwr.F:56-87) --------------------
 // A(:,0:N) <- A(:,0:K) * W,  W real K x N column-major (ld = K) in HOST memory (it comes from the host

@@ -118,6 +118,55 @@ class ShardedOperator:
             pass
 
 
+class ShardedDenseOperator:
+    """This rank's row block of a dense matrix, resident on its GPU (``propack_b200_dense_create_sharded_*``).
+
+    ``A`` is the full (m x n) array (every rank uploads only its own rows ``A[r0:r1]``).  ``synthetic=(seed, table)``
+    evaluates the rows of the BASELINE config-3 matrix on the device instead (``A`` is then just the global shape)."""
+
+    def __init__(self, A, rank: int, world: int, dtype=None, synthetic=None):
+        L = lib()
+        self.rank, self.world = rank, world
+        if synthetic is not None:
+            m, n = A
+            seed, table = synthetic
+            self.dtype, self.pfx, self.shape = np.dtype(np.float64), "d", (int(m), int(n))
+            T = np.ascontiguousarray(table, dtype=np.float64)
+            L.propack_b200_dense_create_synthetic_sharded_d.argtypes = [C.c_int, C.c_int, C.c_ulonglong, C.c_void_p]
+            self.handle = check(L.propack_b200_dense_create_synthetic_sharded_d(int(m), int(n), int(seed), T.ctypes.data_as(C.c_void_p)),
+                                "dense_create_synthetic_sharded")
+        else:
+            A = np.asarray(A)
+            dtype = np.dtype(dtype or A.dtype)
+            if dtype not in PREFIX:
+                dtype = np.dtype(np.complex128 if np.iscomplexobj(A) else np.float64)
+            self.dtype, self.pfx = dtype, PREFIX[dtype]
+            r0, r1 = shard_bounds(A.shape[0], world, rank)
+            self.shape = (int(A.shape[0]), int(A.shape[1]))
+            blk = np.asfortranarray(A[r0:r1].astype(dtype, copy=False))
+            if blk.shape[0] == 0:
+                blk = np.zeros((1, A.shape[1]), dtype=dtype, order="F")
+            fn = getattr(L, f"propack_b200_dense_create_sharded_{self.pfx}")
+            fn.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_long]
+            self.handle = check(fn(self.shape[0], self.shape[1], _p(blk), blk.shape[0]), "dense_create_sharded")
+        self.rows = shard_bounds(self.shape[0], world, rank)
+        self.cols = shard_bounds(self.shape[1], world, rank)
+
+    def bytes_per_product(self, adjoint=False) -> float:
+        return float(lib().propack_b200_op_bytes(C.c_int(self.handle), C.c_int(int(adjoint))))
+
+    def close(self):
+        if self.handle:
+            lib().propack_b200_op_destroy(C.c_int(self.handle))
+            self.handle = 0
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class Solver:
     """A solver session over a (sharded or single-GPU) operator: bases stay in HBM, results come back as this
     rank's row slices."""

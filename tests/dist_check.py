@@ -39,7 +39,8 @@ def run_case(name, A, k, kmax, rank, world, irl=None, tol=1e-12, dense_check=Tru
     m, n = A.shape
     dtype = A.dtype
     u0 = np.random.default_rng(1).uniform(size=m).astype(dtype)
-    op = pdist.ShardedOperator(A, rank, world)
+    dense_op = isinstance(A, np.ndarray)          # row-sharded dense operator (BASELINE configs[2] on N GPUs)
+    op = pdist.ShardedDenseOperator(A, rank, world) if dense_op else pdist.ShardedOperator(A, rank, world)
     lanmax = min(m + 1, n + 1, kmax)
     sv = pdist.Solver(op, lanmax + 1, lanmax)
     sv.set_start(u0)
@@ -55,7 +56,7 @@ def run_case(name, A, k, kmax, rank, world, irl=None, tol=1e-12, dense_check=Tru
     if rank == 0:
         S = r["sigma"]
         eps = np.finfo(dtype).eps
-        e_sig = relerr(S, np.linalg.svd(A.toarray(), compute_uv=False)[:k]) if dense_check else float("nan")
+        e_sig = relerr(S, np.linalg.svd(A if dense_op else A.toarray(), compute_uv=False)[:k]) if dense_check else float("nan")
         res = float(np.max(np.linalg.norm(A @ V - U * S, axis=0)))
         orth = float(max(np.max(np.abs(U.conj().T @ U - np.eye(k))), np.max(np.abs(V.conj().T @ V - np.eye(k)))))
         # the CPU oracle on the same inputs (same start vector): parity of the algorithm, not only of the answer
@@ -78,6 +79,16 @@ def run_case(name, A, k, kmax, rank, world, irl=None, tol=1e-12, dense_check=Tru
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.broadcast(flag, src=0)
     return bool(flag.item())
+
+
+def dense_planted_small(rng, m, n, dtype):
+    """Dense test matrix with a decaying planted spectrum on top of noise (so that the leading triplets converge quickly)."""
+    r = min(m, n, 24)
+    X = rng.standard_normal((m, r)); Y = rng.standard_normal((n, r))
+    A = (X * (2.0 ** -np.arange(r))) @ Y.T + 0.01 * rng.standard_normal((m, n))
+    if np.issubdtype(dtype, np.complexfloating):
+        A = A + 1j * ((rng.standard_normal((m, r)) * (2.0 ** -np.arange(r))) @ rng.standard_normal((n, r)).T)
+    return np.asfortranarray(A.astype(dtype))
 
 
 def c5_pattern(m, n, per=10):
@@ -104,6 +115,11 @@ def main():
     ok &= run_case("d 4000x40 lansvd (ranks without columns)", rand_sparse(rng, 4000, 40, 0.2, np.float64), 5, 41, rank, world)
     ok &= run_case("z 1500x1200 zlansvd", rand_sparse(rng, 1500, 1200, 0.01, np.complex128), 6, 150, rank, world)
     ok &= run_case("d 3000x2000 lansvd_irl", rand_sparse(rng, 3000, 2000, 0.005, np.float64), 6, 60, rank, world, irl=(40, 20), tol=1e-10)
+    # row-sharded dense operators: tall-skinny real with IRL (the config-3 shape in small), complex, and a fat one whose
+    # trailing ranks own no rows
+    ok &= run_case("d dense 5000x96 lansvd_irl", dense_planted_small(rng, 5000, 96, np.float64), 10, 40, rank, world, irl=(40, 20), tol=1e-10)
+    ok &= run_case("z dense 1200x200 zlansvd", dense_planted_small(rng, 1200, 200, np.complex128), 6, 120, rank, world)
+    ok &= run_case("d dense 40x900 lansvd (ranks without rows)", dense_planted_small(rng, 40, 900, np.float64), 5, 41, rank, world)
     # the config-5 shape of the north star (k=100, DLANSVD_IRL dim=300 p=200: restarts, the 101-column restart GEMM)
     rows_large = int(os.environ.get("DIST_CHECK_LARGE_ROWS", "1000000"))
     if rows_large > 0:

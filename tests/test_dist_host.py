@@ -102,6 +102,17 @@ def _gloo_worker(rank, world, port, q):
         part = torch.tensor([float(np.dot(y_loc, y_loc))], dtype=torch.float64)
         dist.all_reduce(part)
         ok = ok and abs(float(part.sqrt()) - np.linalg.norm(A @ x)) < 1e-12 * np.linalg.norm(A @ x)
+        # dense row-sharded operator (ShardedDenseOperator): A x from the gathered n-vector and the local row block;
+        # A^T u as local GEMV^T + all-reduce of the n coefficients, every rank keeping its slice
+        D = rng.standard_normal((m, 24)); xd = rng.standard_normal(24)
+        dn = pdist.slice_len(24, world); d0, d1 = pdist.shard_bounds(24, world, rank)
+        xdf = allgather(xd[d0:d1], dn)
+        yd = pdist.gather_rows(D[r0:r1] @ xdf[:24], m)
+        ok = ok and np.allclose(yd, D @ xd, rtol=0, atol=1e-12)
+        coef = torch.from_numpy(D[r0:r1].T @ u[r0:r1])
+        dist.all_reduce(coef)
+        vd = pdist.gather_rows(coef.numpy()[d0:d1], 24)
+        ok = ok and np.allclose(vd, D.T @ u, rtol=0, atol=1e-10)
         q.put((rank, bool(ok)))
     finally:
         dist.destroy_process_group()

@@ -343,8 +343,12 @@ def test_blasext_level1_matches_oracle(oracle, dtype, n):
     from propack_b200 import f77
     rng = np.random.default_rng(n)
     x, y = rand_vec(rng, n, dtype), rand_vec(rng, n, dtype)
-    tol = TOL[dtype] * 1e-2
+    # the oracle accumulates in the working precision like the reference BLAS (rounding error ~ sqrt(n) eps in single),
+    # the device kernels in double: the bar against the oracle carries that term, the bar against a float64 sum does not
+    tol = max(TOL[dtype] * 1e-2, 4.0 * np.sqrt(n) * np.finfo(dtype).eps)
     assert abs(f77.nrm2(x) - oracle.nrm2(x)) <= tol * oracle.nrm2(x)
+    exact = np.linalg.norm(x.astype(np.complex128 if np.iscomplexobj(x) else np.float64))
+    assert abs(f77.nrm2(x) - exact) <= 4 * np.finfo(dtype).eps * exact
     d_got, d_want = f77.dotc(x, y), oracle.dotc(x, y)
     assert abs(d_got - d_want) <= tol * np.linalg.norm(x) * np.linalg.norm(y)
     alpha = dtype(0.75) if not np.iscomplexobj(x) else dtype(0.75 - 0.5j)

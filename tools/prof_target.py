@@ -29,7 +29,7 @@ for persist in ((1, 0) if os.environ.get("PROF_L2_AB") else (1,)):
             out[tag + "_ms"] = t
             out[tag + "_gbs"] = (op.bytes_per_product(bool(adj)) + 8.0 * m) / t / 1e6
 L.propack_b200_set_option(b"l2_persist", C.c_int(1))
-for l in (16, 64, 256, 300, 537):
+for l in [int(x) for x in os.environ.get("PROF_LS", "16,64,256,300,537").split(",")]:
     t = L.propack_b200_bench_reorth_d(m, l, REPS, 1)
     out[f"reorth_l{l}_ms"] = t
     out[f"reorth_l{l}_gbs"] = 8.0 * m * (2 * l + 3) / t / 1e6
