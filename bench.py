@@ -58,9 +58,15 @@ IRL_P = {"c5": 200, "c5-small": 200, "c3": 100, "c3-small": 50}   # workloads so
 IRL_MAXITER = 50
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel at working size, from the committed
 # `ncu --set full` captures (profiles/r02_ncu_extract.txt); filled in by hand from those files, None = not captured
-NCU_TRAFFIC_BYTES_PER_LAUNCH = {("c5", "spmv"): None, ("c5", "reorth"): None, ("c2", "spmv"): 140.03e6 + 5.3e6, ("c2", "reorth"): None}
+# (SpMV: per product = the 2 column-panel launches of spmv_sell_kernel on config 5, mean of A x and A^T u; reorth: one GEMV
+# pair gemv_t_tma_kernel + gemv_n_kernel at L = 1e7, l = 64 -- 10.485 GB against 10.48 GB algorithmic)
+NCU_TRAFFIC_BYTES_PER_LAUNCH = {("c5", "spmv"): 1.676e9, ("c5", "reorth"): 10.485e9, ("c2", "spmv"): 140.03e6 + 5.3e6, ("c2", "reorth"): None}
+NCU_TRAFFIC_NOTE = {("c5", "spmv"): "dram__bytes_read+write of the 2 panel launches of one product (profiles/r02_ncu_extract_c5.txt [0]+[1] / [6]+[7]); "
+                                    "algorithmic 1.48 GB + the second panel's read-modify-write of y (0.16 GB)",
+                    ("c5", "reorth"): "one GEMV pair at L=1e7, l=64 (profiles/r02_ncu_extract_c5.txt [12]+[13]): 10.485 GB measured vs 10.48 GB algorithmic"}
 CPU_SAMPLE_STEPS = 150  # Lanczos steps of the same problem the in-line cpu_baseline runs (bounded sample, ~10-30 s)
-REF_BUDGET_S = 600.0    # --impl reference: stop adding full CPU solves once the projected run time passes this
+REF_BUDGET_S = 500.0    # --impl reference: stop adding full CPU solves once the projected run time passes this
+SCIPY_START_BEFORE_S = 400.0   # ... and only start the SciPy cross-check (~4 min on config 5's 1/10 replica) this early in the run
 
 
 class DenseSpec:
@@ -312,7 +318,7 @@ def run_reference(args):
         "cpu_baseline": {"value": value, "unit": "steps/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    if not args.no_scipy and time.perf_counter() - t_start < REF_BUDGET_S:
+    if not args.no_scipy and time.perf_counter() - t_start < SCIPY_START_BEFORE_S:
         sc = scipy_svdp_sample(args.workload)
         if sc:
             line["scipy_svdp"] = sc
@@ -446,19 +452,22 @@ def run_ours(args):
     traffic_known = NCU_TRAFFIC_BYTES_PER_LAUNCH
     if aprod_ms >= reorth_ms:
         kname = ("dense APROD = gemv_n_kernel / gemv_t_kernel + gemv_t_finalize over A itself" if isinstance(A, DenseSpec) else
-                 "spmv_kernel (CSR gather SpMV, fused axpy + norm; + spmv_long_kernel on power-law rows)")
+                 "spmv_sell_kernel (sliced jagged-ELL gather SpMV, fused axpy + norm; one launch per column panel of the gathered "
+                 "vector; + spmv_long_kernel on power-law rows)")
         roofline = {"bound": "hbm", "kernel": kname, "achieved": spmv_gbs, "peak": peak, "unit": "GB/s", "frac": spmv_gbs / peak,
                     "peak_source": peak_src, "frac_of_nominal_8000": spmv_gbs / 8000.0,
-                    "traffic": traffic_known.get((args.workload, "spmv")), "algorithmic_bytes": spmv_bytes,
+                    "traffic": traffic_known.get((args.workload, "spmv")), "traffic_note": NCU_TRAFFIC_NOTE.get((args.workload, "spmv")),
+                    "algorithmic_bytes": spmv_bytes,
                     "algorithmic_bytes_per_launch": spmv_bytes / max(pctr["nopx"], 1), "kernel_ms_in_solve": aprod_ms,
                     "share_of_solve": aprod_ms / tot_ms,
                     "note": ("random-column gathers bound this kernel by the L1TEX wavefront rate, not HBM: the measured gather floor is "
                              "~51% of the HBM peak at 10 nnz/row (profiles/r01_spmv_lab.md)") if not isinstance(A, DenseSpec) else "",
                     "how": "CUDA-event phase timers on the library stream in one extra profiled solve of the same workload"}
     else:
-        roofline = {"bound": "hbm", "kernel": "reorthogonalisation GEMV pair (gemv_t_kernel + gemv_t_finalize + gemv_n_kernel)",
+        roofline = {"bound": "hbm", "kernel": "reorthogonalisation GEMV pair (gemv_t_tma_kernel [TMA-staged; gemv_t_kernel for short vectors] + gemv_t_finalize + gemv_n_kernel)",
                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
                     "frac_of_nominal_8000": achieved / 8000.0, "traffic": traffic_known.get((args.workload, "reorth")),
+                    "traffic_note": NCU_TRAFFIC_NOTE.get((args.workload, "reorth")),
                     "algorithmic_bytes": rb, "kernel_ms_in_solve": reorth_ms, "share_of_solve": reorth_ms / tot_ms,
                     "how": "CUDA-event phase timers on the library stream in one extra profiled solve of the same workload"}
     # isolated kernels (device-resident synthetic operands, L2 flushed between launches)
@@ -487,7 +496,7 @@ def run_ours(args):
     Upin = torch.empty((k + 1, m), dtype=tdt).pin_memory().numpy().T
     Vpin = torch.empty((k + 1, n), dtype=tdt).pin_memory().numpy().T
 
-    e2e_create = []
+    e2e_create, e2e_call = [], []
 
     def solve_e2e():
         t0 = time.perf_counter()
@@ -502,12 +511,14 @@ def run_ours(args):
             op2.handle, op2._cb, op2.dtype, op2.pfx, op2.shape = h, None, np.dtype(A.dtype), pfx, (m, n)
             op2.iparm = np.array([h, 0], dtype=np.int32); op2.parm = np.zeros(2, dtype=A.dtype)
         e2e_create.append(time.perf_counter() - t0)
+        t1 = time.perf_counter()
         if args.workload in IRL_P:
             r = f77.lansvd_irl(op2, k, kmax, p=IRL_P[args.workload], maxiter=IRL_MAXITER, tol=tol, u0=u0p, cgs=True, U=Upin, V=Vpin)
         else:
             r = f77.lansvd(op2, k, kmax, tol=tol, u0=u0p, cgs=True, U=Upin, V=Vpin)
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
+        e2e_call.append(time.perf_counter() - t1)
         op2.close()
         return dt, r
 
@@ -550,6 +561,7 @@ def run_ours(args):
             "e2e": {"value": e2e_val, "unit": "steps/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "time_to_k_triplets_s": float(np.mean(e2e_t)),
                     "operator_create_s": float(np.mean(e2e_create[1:])) if len(e2e_create) > 1 else None,
+                    "driver_call_s": float(np.mean(e2e_call[1:])) if len(e2e_call) > 1 else None,
                     "path": "propack_b200_csr_create_d + dlansvd[_irl]_ (Fortran ABI; host CSR, start vector and the caller's U,V result buffers in pinned memory; U,V,sigma copied back)"},
             "roofline": roofline,
             "reorth": {"achieved_gbs_in_solve": achieved, "frac": achieved / peak, "reorth_ms_in_solve": reorth_ms,

@@ -96,13 +96,16 @@ gemm_tall_kernel(long Mr, int N, int K, R* A, long lda, const double* __restrict
       __syncthreads();          // ... and everybody's; also: everybody is done reading the other buffer (chunk ch-1)
       if (ch + 1 < nchunks) { stage_w(ch + 1, (ch + 1) & 1); load_a(ch + 1, a_nxt); }
       const double* wb = wsm + (ch & 1) * CHUNK;
+      const int ks_here = min(GK_KS, ksteps - ch * GK_KS);   // the last chunk is not padded with zero k-steps (warp-uniform bound)
 #pragma unroll
       for (int s = 0; s < GK_KS; ++s)
+        if (s < ks_here) {
 #pragma unroll
-        for (int j = 0; j < NT; ++j) {
-          const double b = wb[(s * NT + j) * 32 + lane];
+          for (int j = 0; j < NT; ++j) {
+            const double b = wb[(s * NT + j) * 32 + lane];
 #pragma unroll
-          for (int mt = 0; mt < MT; ++mt) dmma(c[mt][j][0], c[mt][j][1], a_cur[s][mt], b);
+            for (int mt = 0; mt < MT; ++mt) dmma(c[mt][j][0], c[mt][j][1], a_cur[s][mt], b);
+          }
         }
 #pragma unroll
       for (int s = 0; s < GK_KS; ++s)

@@ -18,7 +18,7 @@ except Exception as e: print('bench parse failed', e)
 P
 tail -3 $O/r02_bench_c5_n$N.err
 if [ "${RUN_C3:-1}" = "1" ]; then
-timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29513 bench.py --gpus $N --workload c3 --steps 2 --warmup 1 > $O/r02_bench_c3_n$N.json 2> $O/r02_bench_c3_n$N.err; echo "bench c3 N=$N rc=$?"
+timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29513 bench.py --gpus $N --workload c3 --steps 1 --warmup 1 > $O/r02_bench_c3_n$N.json 2> $O/r02_bench_c3_n$N.err; echo "bench c3 N=$N rc=$?"
 python - <<P
 import json
 try:
