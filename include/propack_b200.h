@@ -337,6 +337,9 @@ int propack_b200_host_ritz_bounds_d(int j, const double* alpha, const double* be
 /* host-only test hook: the (dim+1) x k and dim x k matrices that dritzvec (double/dritzvec.F:116-193) multiplies the Lanczos
  * bases with, by the reference route (method 0) or the fast route (method 1; returns 1 when it declines) */
 int propack_b200_host_ritz_vectors_d(int dim, const double* alpha, const double* beta, int k, int method, double* WU, double* WV);
+/* host-only test hook: the shifted QR sweeps of one implicit restart (double/dlansvd_irl.F:350-363, dbsvd.F:5-82) accumulating
+ * P ((dim+1) x (dim+1)) and Q (dim x dim); nthreads = 0 is the sequential reference order, >= 1 the row-parallel route */
+int propack_b200_host_restart_sweeps_d(int dim, int k, const double* shift, double* alpha, double* beta, double* P, double* Q, int nthreads);
 int propack_b200_init(void);                         /* create the context on the current device; 0 or negative */
 int propack_b200_set_stream(void* cuda_stream);      /* run on a caller stream (e.g. torch's current stream) */
 int propack_b200_set_lapack(const char* path);       /* shared object providing {d,s}bdsqr / {d,s}bdsdc */

@@ -1146,6 +1146,24 @@ int propack_b200_host_ritz_vectors_d(int dim, const double* alpha, const double*
   PB_API_CATCH(return code__)
 }
 
+// Host-only test hook: the p = dim-k shifted QR sweeps of an implicit restart (dlansvd_irl.F:350-363) on the bidiagonal
+// (alpha, beta), accumulating P ((dim+1)^2) and Q (dim^2) from the identity.  nthreads = 0: the reference's sequential
+// dbsvdstep accumulation (rotation by rotation); nthreads >= 1: the recorded-rotation, row-parallel route the driver uses.
+int propack_b200_host_restart_sweeps_d(int dim, int k, const double* shift, double* alpha, double* beta, double* P, double* Q, int nthreads) {
+  PB_API_TRY
+  std::fill(P, P + (size_t)(dim + 1) * (dim + 1), 0.0);
+  std::fill(Q, Q + (size_t)dim * dim, 0.0);
+  for (int i = 0; i <= dim; ++i) P[(size_t)i * (dim + 2)] = 1.0;
+  for (int i = 0; i < dim; ++i) Q[(size_t)i * (dim + 1)] = 1.0;
+  if (nthreads <= 0) {
+    for (int i = dim; i >= k + 1; --i) host::bidiag_shift_sweep<double>(dim + 1, dim, i, shift[dim - i], alpha, beta, P, dim + 1, Q, dim);
+  } else {
+    host::restart_sweeps<double>(dim, k, shift, alpha, beta, P, Q, nthreads);
+  }
+  return 0;
+  PB_API_CATCH(return code__)
+}
+
 // ---- runtime --------------------------------------------------------------------------------------------------
 int propack_b200_init(void) {
   PB_API_TRY

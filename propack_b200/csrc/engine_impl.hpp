@@ -409,8 +409,9 @@ int Engine<T>::lansvd_irl(bool smallest, bool jobu, bool jobv, int& dim, int p, 
       std::fill(Q.begin(), Q.end(), zero);
       for (int i = 0; i <= dim; ++i) P[(size_t)i * (dim + 2)] = one;
       for (int i = 0; i < dim; ++i) Q[(size_t)i * (dim + 1)] = one;
-      for (int i = dim; i >= k + 1; --i)
-        host::bidiag_shift_sweep<R>(dim + 1, dim, i, shift[dim - i], a.data(), b.data(), P.data(), dim + 1, Q.data(), dim);
+      // (scalar recurrences first, then the ~2 p dim recorded rotations applied row-parallel by a few host threads:
+      // host_algebra.hpp::restart_sweeps -- bit-identical to the sequential accumulation)
+      host::restart_sweeps<R>(dim, k, shift.data(), a.data(), b.data(), P.data(), Q.data(), host_threads());
       // U(:,1:k+1) <- U(:,1:dim+1) P(:,1:k+1);  V(:,1:k) <- V(:,1:dim) Q(:,1:k)  (:387-395)
       k_gemm_tall<T>(c, m, k + 1, dim + 1, U, ldu, P.data());   // P is (dim+1)x(dim+1), ld = dim+1 = K
       k_gemm_tall<T>(c, n, k, dim, V, ldv, Q.data());           // Q is dim x dim, ld = dim = K

@@ -21,6 +21,7 @@
 //   - float / complex-float bases are widened to FP64 on load (same kernel, half the bytes).
 // Arithmetic intensity 2KN/(w(K+N)) ~ N/4 flop/B: FP64-pipe bound for N >~ 25.
 #include <algorithm>
+#include <cstdlib>
 #include <vector>
 
 #include "kernels.cuh"
@@ -137,16 +138,23 @@ copy_cols_kernel(long Mr, int N, const R* __restrict__ src, long lds, R* __restr
 
 template <class R, int NT, int MT>
 void launch_slab(Context& c, long Mr, int N, int K, R* A, long lda, const double* Wp, int nt_total, int nt0, R* dst, long ldd) {
-  const int grid = c.grid_for(Mr, 64 * MT, 2);
   constexpr size_t smem = sizeof(double) * 2 * gk_ks<MT>() * NT * 32;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static int occ = 0;            // resident CTAs per SM of this instantiation (registers / shared memory), at most 2
+  if (occ == 0) {
     PB_CUDA(cudaFuncSetAttribute(gemm_tall_kernel<R, NT, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
+    PB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, gemm_tall_kernel<R, NT, MT>, kThreads, smem));
+    occ = std::min(2, std::max(1, occ));
   }
+  const int grid = c.grid_for(Mr, 64 * MT, occ);
   gemm_tall_kernel<R, NT, MT><<<grid, kThreads, smem, c.stream>>>(Mr, N, K, A, lda, Wp, nt_total, nt0, dst, ldd);
   PB_LAUNCH_CHECK();
   c.ctr.launches += 1;
+}
+
+// PROPACK_B200_GEMM_MT2=1: two m-tiles per warp for the 10- and 13-tile widths (each W fragment feeds two DMMAs; 1 CTA/SM)
+inline bool gemm_mt2() {
+  static const bool on = [] { const char* e = std::getenv("PROPACK_B200_GEMM_MT2"); return e && e[0] == '1'; }();
+  return on;
 }
 
 template <class R>
@@ -154,8 +162,10 @@ void slab(Context& c, int nt, long Mr, int N, int K, R* A, long lda, const doubl
   if (nt <= 2) launch_slab<R, 2, 4>(c, Mr, N, K, A, lda, Wp, nt_total, nt0, dst, ldd);
   else if (nt <= 4) launch_slab<R, 4, 4>(c, Mr, N, K, A, lda, Wp, nt_total, nt0, dst, ldd);
   else if (nt <= 7) launch_slab<R, 7, 2>(c, Mr, N, K, A, lda, Wp, nt_total, nt0, dst, ldd);
-  else if (nt <= 10) launch_slab<R, 10, 1>(c, Mr, N, K, A, lda, Wp, nt_total, nt0, dst, ldd);
-  else if (nt <= 13) launch_slab<R, 13, 1>(c, Mr, N, K, A, lda, Wp, nt_total, nt0, dst, ldd);
+  else if (nt <= 10) { if (gemm_mt2()) launch_slab<R, 10, 2>(c, Mr, N, K, A, lda, Wp, nt_total, nt0, dst, ldd);
+                       else launch_slab<R, 10, 1>(c, Mr, N, K, A, lda, Wp, nt_total, nt0, dst, ldd); }
+  else if (nt <= 13) { if (gemm_mt2()) launch_slab<R, 13, 2>(c, Mr, N, K, A, lda, Wp, nt_total, nt0, dst, ldd);
+                       else launch_slab<R, 13, 1>(c, Mr, N, K, A, lda, Wp, nt_total, nt0, dst, ldd); }
   else launch_slab<R, 16, 1>(c, Mr, N, K, A, lda, Wp, nt_total, nt0, dst, ldd);
 }
 

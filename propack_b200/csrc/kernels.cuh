@@ -26,6 +26,8 @@ template <class T> void k_zero(Context& c, long n, T* x);          // pdzero dbl
 template <class T>
 void k_scal_push(Context& c, long n, long ld, T* x, real_t<T> a, void** bases_dev, int rank, int world, unsigned long long epoch,
                  T* self_slice);
+template <class T>
+void k_scal_local(Context& c, long n, T* x, real_t<T> a, T* self_slice, unsigned long long* epoch_dev, unsigned long long epoch);
 void k_wait_flags(Context& c, const unsigned long long* flags, unsigned int src_mask, unsigned long long epoch);
 // x(i) <- LAPACK xLARNV(idist=2, iseed) stream element offset+i, i=0..n-1 ; publish ||x||  (dgetu0.F:69-70).
 // `offset` = global index of this rank's first element in a row-sharded run (0 on one GPU).

@@ -69,9 +69,11 @@ push_kernel(long n, long ld, const T* __restrict__ x, void** bases, int rank, in
 // x <- a*x and a copy into this rank's own slice of its gather buffer (main-stream half of the push)
 template <class T>
 __global__ void __launch_bounds__(kThreads)
-scal_local_kernel(long n, T* __restrict__ x, real_t<T> a, T* __restrict__ self) {
+scal_local_kernel(long n, T* __restrict__ x, real_t<T> a, T* __restrict__ self, unsigned long long* epoch_out, unsigned long long epoch) {
   constexpr int VEC = Pack<T>::N;
   const long np = (n + VEC - 1) / VEC;
+  // copy-engine transport: the arrival flags the peers receive are copies of this word (stream-ordered behind the slice)
+  if (epoch_out != nullptr && blockIdx.x == 0 && threadIdx.x == 0) *epoch_out = epoch;
   for (long i = (long)blockIdx.x * kThreads + threadIdx.x; i < np; i += (long)gridDim.x * kThreads) {
     Pack<T> p = ld_pack(x + i * VEC);
 #pragma unroll
@@ -230,7 +232,7 @@ template <class T>
 void k_scal_push(Context& c, long n, long ld, T* x, real_t<T> a, void** bases_dev, int rank, int world, unsigned long long epoch,
                  T* self_slice) {
   if (n > 0) {
-    scal_local_kernel<T><<<l1_grid<T>(c, n), kThreads, 0, c.stream>>>(n, x, a, self_slice);
+    scal_local_kernel<T><<<l1_grid<T>(c, n), kThreads, 0, c.stream>>>(n, x, a, self_slice, nullptr, 0ull);
     PB_LAUNCH_CHECK();
     c.ctr.launches += 1;
   }
@@ -239,6 +241,14 @@ void k_scal_push(Context& c, long n, long ld, T* x, real_t<T> a, void** bases_de
   PB_CUDA(cudaStreamWaitEvent(c.stream2, c.ev_fork, 0));
   const int grid = (int)std::min<long>(push_ctas(), std::max<long>(1, ((n + Pack<T>::N - 1) / Pack<T>::N + kThreads - 1) / kThreads));
   push_kernel<T><<<grid, kThreads, 0, c.stream2>>>(n, ld, x, bases_dev, rank, world, c.tickets8, epoch);
+  PB_LAUNCH_CHECK();
+  c.ctr.launches += 1;
+}
+// Main-stream half of the copy-engine all-gather: x <- a*x, copy into this rank's own slice of its gather buffer, and
+// the epoch word the flag copies will carry (launched even for n = 0: the flags must still be raised).
+template <class T>
+void k_scal_local(Context& c, long n, T* x, real_t<T> a, T* self_slice, unsigned long long* epoch_dev, unsigned long long epoch) {
+  scal_local_kernel<T><<<l1_grid<T>(c, std::max<long>(n, 1)), kThreads, 0, c.stream>>>(n, x, a, self_slice, epoch_dev, epoch);
   PB_LAUNCH_CHECK();
   c.ctr.launches += 1;
 }
@@ -289,6 +299,7 @@ template <class T> void k_larnv_nrm(Context& c, long n, T* x, const int iseed[4]
   template void k_scal<T>(Context&, long, T*, real_t<T>);                         \
   template void k_zero<T>(Context&, long, T*);                                    \
   template void k_scal_push<T>(Context&, long, long, T*, real_t<T>, void**, int, int, unsigned long long, T*); \
+  template void k_scal_local<T>(Context&, long, T*, real_t<T>, T*, unsigned long long*, unsigned long long); \
   template void k_axpy_nrm<T>(Context&, long, T, const T*, T*, Pending*);         \
   template void k_dotc<T>(Context&, long, const T*, const T*, Pending*);          \
   template void k_nrm2<T>(Context&, long, const T*, Pending*);                    \

@@ -109,3 +109,34 @@ def test_fast_ritz_vector_matrices_are_singular_vectors_of_B(lanczos_bidiagonal,
     su = np.sign(np.sum(U0 * U1, axis=0))
     assert np.all(su != 0)
     assert np.max(np.abs(U1 * su - U0)) < 1e-9 and np.max(np.abs(V1 * su - V0)) < 1e-9
+
+
+def test_restart_sweeps_row_parallel_is_bit_identical():
+    """The implicit-restart rotation accumulation (dlansvd_irl.F:350-363): the recorded-rotation, row-parallel route of the
+    driver equals the sequential dbsvdstep accumulation bit for bit, for 1 and several host threads, and P^T B Q is the
+    updated bidiagonal."""
+    import ctypes as C
+    from propack_b200 import _lib
+    L = _lib.lib()
+    fn = L.propack_b200_host_restart_sweeps_d
+    fn.argtypes = [C.c_int, C.c_int] + [C.c_void_p] * 5 + [C.c_int]
+    rng = np.random.default_rng(7)
+    for dim, k in ((12, 5), (60, 20), (300, 100)):
+        a0 = rng.uniform(0.5, 2.0, dim + 1); b0 = rng.uniform(0.1, 1.0, dim + 1)
+        B = np.zeros((dim + 1, dim)); B[np.arange(dim), np.arange(dim)] = a0[:dim]; B[np.arange(1, dim + 1), np.arange(dim)] = b0[:dim]
+        shift = np.sort(np.linalg.svd(B, compute_uv=False))[:dim - k][::-1].copy()      # p exact shifts, largest first like the driver
+        shift = np.concatenate([shift, np.zeros(k + 1)])
+        out = {}
+        for nt in (0, 1, 5):
+            a, b = a0.copy(), b0.copy()
+            P = np.zeros((dim + 1, dim + 1), order="F"); Q = np.zeros((dim, dim), order="F")
+            assert fn(dim, k, shift.ctypes.data, a.ctypes.data, b.ctypes.data, P.ctypes.data, Q.ctypes.data, nt) == 0
+            out[nt] = (a, b, P, Q)
+        for nt in (1, 5):
+            for x, y in zip(out[0], out[nt]):
+                assert np.array_equal(x, y)
+        a, b, P, Q = out[0]
+        assert np.max(np.abs(P.T @ P - np.eye(dim + 1))) < 1e-13 and np.max(np.abs(Q.T @ Q - np.eye(dim))) < 1e-13
+        Bp = P.T @ B @ Q
+        assert np.max(np.abs(np.diag(Bp)[:k] - a[:k])) < 1e-12 * np.abs(a0).max() * dim
+        assert np.max(np.abs(np.diag(Bp, -1)[:k - 1] - b[:k - 1])) < 1e-12 * np.abs(a0).max() * dim

@@ -33,6 +33,9 @@ for st in settings:
     kv = dict(x.split("=") for x in st.split(","))
     os.environ["PROPACK_B200_SPMV_PHASES"] = kv.get("PHASES", "4")
     os.environ["PROPACK_B200_PUSH_CTAS"] = kv.get("PUSH", "32")
+    os.environ["PROPACK_B200_PUSH"] = kv.get("MODE", "ce")            # ce (copy engines, default) | sm (push kernel)
+    os.environ["PROPACK_B200_PUSH_CHAINS"] = kv.get("CHAINS", "2")    # concurrent chains of peer copies in the push graph
+    os.environ["PROPACK_B200_PUSH_GRAPH"] = kv.get("GRAPH", "1")      # 0: plain stream-ordered copies instead of the CUDA graph
     op = pdist.ShardedOperator(A, rank, world)
     sv = pdist.Solver(op, lanmax + 1, lanmax)
 
