@@ -690,18 +690,24 @@ def run_ours_sharded(args):
             "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": wl_dtype(args.workload)[0], "data": "synthetic",
             "config": config_dict(args.workload, A, k, kmax, tol),
-            "parallelism": (f"rows of A and U, and V-vectors, block-sharded over {world} GPUs; the SpMV input is pushed slice by slice over "
-                            f"NVLink peer memory by a thin side-stream kernel while the phase-split SpMV consumes the slices that have "
-                            f"landed; all-reduce of reorthogonalisation coefficients and norm partials fused into the producing kernels "
-                            f"(NCCL for the un-staged products); collectives_total counts the NCCL calls that remain"),
+            "parallelism": ((f"rows of the dense A and of U, and V-vectors, block-sharded over {world} GPUs; A x = NCCL all-gather of the "
+                             f"n-vector + local GEMV, A^T u = local GEMV^T + NCCL all-reduce of the n coefficients; reorthogonalisation "
+                             f"coefficients and norm partials all-reduced inside the producing kernels over NVLink peer memory") if dense else
+                            (f"rows of A and U, and V-vectors, block-sharded over {world} GPUs; the SpMV input travels slice by slice over "
+                             f"NVLink by copy engines (a CUDA graph of chained peer copies + arrival-flag copies on a side stream) while the "
+                             f"phase-split SpMV consumes the slices that have landed; all-reduce of reorthogonalisation coefficients and "
+                             f"norm partials fused into the producing kernels (NCCL for the un-staged products); collectives_total counts "
+                             f"the NCCL calls that remain")),
             "time_to_k_triplets_s": total_ms / args.steps / 1e3, "lanczos_steps_per_solve": ctr["nsteps"], "converged": kc,
             "info": info, "sigma_1": float(sigma[0]) if kc else None, "sigma_k": float(sigma[-1]) if kc else None,
             "gpu_launches": int(launches), "host_syncs_per_solve": ctr["host_syncs"],
             "collectives_total": {"allreduce": nar.value, "allgather": nag.value, "allgather_gbytes": agb.value / 1e9},
             "e2e": {"value": e2e_val, "unit": "steps/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "time_to_k_triplets_s": float(np.mean(e2e_t)) if e2e_t else None,
-                    "path": "per rank: propack_b200_csr_create_sharded_d (pinned host shard) + solver session + local U,V slices and "
-                            "sigma copied back; bytes are per rank"},
+                    "path": ("per rank: propack_b200_dense_create_synthetic_sharded_d (this rank's rows generated on the device) + solver "
+                             "session + local U,V slices and sigma copied back; bytes are per rank") if dense else
+                            ("per rank: propack_b200_csr_create_sharded_d (pinned host shard) + solver session + local U,V slices and "
+                             "sigma copied back; bytes are per rank")},
             "roofline": None, "phases_ms_profiled_solve": ph, "profiled_solve_ms": pms, "clocks": clk,
         }
         sys.stdout.flush()

@@ -343,7 +343,7 @@ int propack_b200_host_restart_sweeps_d(int dim, int k, const double* shift, doub
 int propack_b200_init(void);                         /* create the context on the current device; 0 or negative */
 int propack_b200_set_stream(void* cuda_stream);      /* run on a caller stream (e.g. torch's current stream) */
 int propack_b200_set_lapack(const char* path);       /* shared object providing {d,s}bdsqr / {d,s}bdsdc */
-int propack_b200_set_option(const char* name, int value); /* "peer_timeout_s": give up on a silent peer rank after this many seconds (default 30) */
+int propack_b200_set_option(const char* name, int value); /* "peer_timeout_s": give up on a silent peer rank after this many seconds (default 30); "bench_skip_gather": measurement only */
 void propack_b200_release_cache(void);               /* free the Krylov-basis buffers parked for reuse by the next driver call of the same shape */
 void propack_b200_set_profile(int on);               /* per-phase CUDA-event timers (adds synchronisation) */
 void propack_b200_reset_counters(void);

@@ -1189,6 +1189,7 @@ int propack_b200_set_option(const char* name, int value) {
   Context& c = Context::get();
   const std::string n = name ? name : "";
   if (n == "peer_timeout_s") { c.set_peer_timeout(value); return 0; }
+  if (n == "bench_skip_gather") { bench_skip_gather() = value != 0; return 0; }   // measurement only, see engine.hpp
   throw std::runtime_error("propack_b200: unknown option '" + n + "'");
   PB_API_CATCH(return code__)
 }

@@ -45,6 +45,10 @@ inline int host_threads() {
   return n;
 }
 
+// measurement only (set_option("bench_skip_gather", 1) + propack_b200_bench_spmv on a row-sharded operator): time the local
+// panel launches alone, on whatever the gather buffer holds, without the all-gather of the input vector
+inline bool& bench_skip_gather() { static bool v = false; return v; }
+
 inline void set_scalar(float& s, double re, double) { s = (float)re; }
 inline void set_scalar(double& s, double re, double) { s = re; }
 template <class R> inline void set_scalar(cplx<R>& s, double re, double im) { s = cplx<R>((R)re, (R)im); }
@@ -115,6 +119,10 @@ template <class T> struct PanelSet {
   std::vector<std::unique_ptr<Panel>> panels;
   long nnz = 0;
   int rows = 0;
+  // row-sharded operands: all panels in one launch (sell.cu: spmv_sell_fused_kernel) when no panel has long rows and the
+  // kernel fits beside the push kernel; PROPACK_B200_SPMV_FUSED_PHASES=0 keeps one launch per panel
+  SellPanelPack<T> pack;
+  DeviceBuffer<int> pack_wstart;
   // Split the CSR (device pointers) into G panels: panel of column c = ring distance of (c / ld) behind `rank`, / (P/G).
   // Returns the validation status of k_csr_split_phases (0 = ok).
   int build(Context& c, int rows_, long width, long nnz_, const int* rp, const int* ci, const T* va, long ld, int P, int rank, int G,
@@ -148,12 +156,29 @@ template <class T> struct PanelSet {
           if (src != rank) pn.src_mask |= 1u << src;
         }
     }
+    pack = SellPanelPack<T>();
+    const char* e = std::getenv("PROPACK_B200_SPMV_FUSED_PHASES");
+    if (P > 1 && G > 1 && G <= kSellMaxPanels && spmv_use_sell() && !(e && e[0] == '0')) {
+      bool ok = sell_fused_fits<T>(c, panels[0]->S.sell.dev.grid);
+      for (int g = 0; g < G; ++g) ok = ok && panels[g]->S.csr.n_long == 0 && panels[g]->S.sell.dev.grid == panels[0]->S.sell.dev.grid;
+      if (ok) {
+        pack.G = G;
+        pack.grid = panels[0]->S.sell.dev.grid;
+        sell_plan_partition(c, rows, rp, pack.grid, pack_wstart);
+        pack.wstart = pack_wstart.p;
+        for (int g = 0; g < G; ++g) { pack.S[g] = panels[g]->S.sell.dev; pack.mask[g] = panels[g]->src_mask; }
+      }
+    }
     return 0;
   }
   // y = sum_g A_g x + coef*prev, ||y||.  flags != null: panel g first waits for the arrival flags of its sources.
   void apply(Context& c, bool conj, const T* x, T* y, R coef, const T* prev, Pending* nrm, const unsigned long long* flags,
              unsigned long long epoch) {
     const size_t G = panels.size();
+    if (pack.G > 0 && flags != nullptr) {   // staged row-sharded product: one launch, the panels wait for their sources in-kernel
+      k_spmv_sell_fused<T>(c, pack, conj, x, y, coef, prev, nrm, flags, epoch);
+      return;
+    }
     for (size_t g = 0; g < G; ++g) {
       Panel& pn = *panels[g];
       const unsigned int mask = flags ? pn.src_mask : 0u;
@@ -337,7 +362,7 @@ template <class T> struct ShardedCsrOperator : LinOp<T> {
     // staged: the slices are being pushed by the producers (stage_scaled); each panel waits only for its own sources.
     // (nrm != nullptr: the cross-rank norm reduction that follows is what makes reusing the buffer safe.)
     const bool staged = staged_valid[d] && staged_ptr[d] == x && nrm != nullptr;
-    if (!staged) cm.allgather(x, xfull[d], sizeof(T) * (size_t)ld_of(d), c.stream);
+    if (!staged && !bench_skip_gather()) cm.allgather(x, xfull[d], sizeof(T) * (size_t)ld_of(d), c.stream);
     staged_valid[d] = false;
     sets[d].apply(c, /*conj=*/adjoint, xfull[d], y, coef, prev, nrm, staged ? flags(d) : nullptr, epoch[d]);
   }

@@ -35,12 +35,13 @@ scal_kernel(long n, T* __restrict__ x, real_t<T> a) {
 //   destination's arrival flag is raised as soon as ITS copy is complete system-wide -- so slices land at a consumer in
 //   the order rank-1, rank-2, ... and its phase-split SpMV (sell.cu) starts on the early ones while the rest is in flight.
 // The push is NVLink-bound, not SM-bound: a thin grid leaves the SMs to the SpMV that runs concurrently.
-template <class T>
-__global__ void __launch_bounds__(kThreads)
+// (at most 64 registers: the kernel must fit the one CTA slot per SM that the flag-polling SpMV CTAs leave free, or the
+// consumers would spin on slices nobody can send)
+template <class T, int PU>   // PU = packs in flight per thread
+__global__ void __launch_bounds__(kThreads, 4)
 push_kernel(long n, long ld, const T* __restrict__ x, void** bases, int rank, int world, unsigned int* tickets,
             unsigned long long epoch) {
   constexpr int VEC = Pack<T>::N;
-  constexpr int PU = 4;   // packs in flight per thread
   __shared__ bool is_last;
   const long np = (n + VEC - 1) / VEC;
   const long stride = (long)gridDim.x * kThreads;
@@ -228,6 +229,10 @@ inline int push_ctas() {   // read at every call: cheap, and lets one process co
   const int v = e ? std::atoi(e) : 32;
   return std::min(148, std::max(1, v));
 }
+inline int push_depth() {
+  const char* e = std::getenv("PROPACK_B200_PUSH_DEPTH");
+  return e ? std::atoi(e) : 4;
+}
 template <class T>
 void k_scal_push(Context& c, long n, long ld, T* x, real_t<T> a, void** bases_dev, int rank, int world, unsigned long long epoch,
                  T* self_slice) {
@@ -240,7 +245,8 @@ void k_scal_push(Context& c, long n, long ld, T* x, real_t<T> a, void** bases_de
   PB_CUDA(cudaEventRecord(c.ev_fork, c.stream));
   PB_CUDA(cudaStreamWaitEvent(c.stream2, c.ev_fork, 0));
   const int grid = (int)std::min<long>(push_ctas(), std::max<long>(1, ((n + Pack<T>::N - 1) / Pack<T>::N + kThreads - 1) / kThreads));
-  push_kernel<T><<<grid, kThreads, 0, c.stream2>>>(n, ld, x, bases_dev, rank, world, c.tickets8, epoch);
+  if (push_depth() >= 8) push_kernel<T, 8><<<grid, kThreads, 0, c.stream2>>>(n, ld, x, bases_dev, rank, world, c.tickets8, epoch);
+  else push_kernel<T, 4><<<grid, kThreads, 0, c.stream2>>>(n, ld, x, bases_dev, rank, world, c.tickets8, epoch);
   PB_LAUNCH_CHECK();
   c.ctr.launches += 1;
 }

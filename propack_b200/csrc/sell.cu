@@ -92,31 +92,12 @@ template <class T> __device__ inline T ldcs_(const T* p) { return ld_cs_pred(p, 
 constexpr int kSellAcc = kSellModeAcc;      // y += A_g x   (a later panel of a split product)
 constexpr int kSellFinal = kSellModeFinal;  // apply  + coef*prev, publish ||y||
 
-// U = independent (ci -> x) gather chains per lane per batch; MINB = CTAs per SM the register budget is capped for
-// (U = 8: <= 51 registers, 5 CTAs = 40 warps per SM; U = 4: <= 32 registers, 8 CTAs = 64 warps per SM)
-template <class T, bool CONJ, int U, int MINB>
-__global__ void __launch_bounds__(kThreads, MINB)
-spmv_sell_kernel(SellDevice<T> S, const T* __restrict__ x, T* y, real_t<T> coef, const T* __restrict__ prev, ReduceWs ws,
-                 int want_norm, int mode, const unsigned long long* flags, unsigned int src_mask, unsigned long long epoch) {
-  __shared__ double red[32];
-  const int lane = threadIdx.x & 31;
-  const unsigned below = (1u << lane) - 1u;
-  if (src_mask != 0u) {
-    // row-sharded run: the slices of the ranks in src_mask must have landed (epoch `epoch`) before x is gathered
-    if (threadIdx.x < 32 && ((src_mask >> threadIdx.x) & 1u)) {
-      const long long t0 = clock64();
-      while (*reinterpret_cast<const volatile unsigned long long*>(flags + threadIdx.x) < epoch) {
-        if (clock64() - t0 > ws.timeout_cycles) { *ws.host_err = 1u; break; }   // a peer died; do not hang the GPU
-      }
-      __threadfence();
-    }
-    __syncthreads();
-  }
-  const int wid = blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
-  long s = __ldg(S.wstart + wid);
-  const long s_end = __ldg(S.wstart + wid + 1);
-  double nrm = 0.0;
-  const bool acc_mode = (mode & kSellAcc) != 0, final_mode = (mode & kSellFinal) != 0;
+// One warp's pass over the slices [s, s_end) of one operand S: lane = row, U independent (ci -> x) gather chains per lane
+// per batch.  acc_mode: y += (a later panel of a split product); final_mode: + coef*prev and |y|^2 into nrm.
+template <class T, bool CONJ, int U>
+__device__ __forceinline__ void sell_range(const SellDevice<T>& S, long s, const long s_end, const T* __restrict__ x, T* y,
+                                           real_t<T> coef, const T* __restrict__ prev, const bool acc_mode, const bool final_mode,
+                                           const int lane, const unsigned below, double& nrm) {
   // lane state of the current slice: row length byte (0xFF = long row, done elsewhere) and the slice's first entry
   int lenb = 0;
   long long base = 0;
@@ -140,6 +121,13 @@ spmv_sell_kernel(SellDevice<T> S, const T* __restrict__ x, T* y, real_t<T> coef,
     const int maxlen = (int)__reduce_max_sync(0xffffffffu, (unsigned)len);
     const int* cis = S.ci + base;      // this slice's entries; offsets inside a slice fit 32 bits (<= 32 * kSellLong)
     const T* vas = S.va + base;
+    // the epilogue operands are requested up front, under the gathers: with the short rows of a panel of a row-sharded
+    // operand (2-3 entries) the slice is latency-bound, and a y / prev load issued after the loop would add a full
+    // memory round trip to every slice
+    const bool live = row < S.rows && !is_long;
+    T y_in = zero_<T>(), p_in = zero_<T>();
+    if (live && acc_mode) y_in = y[row];
+    if (live && final_mode && prev != nullptr) p_in = ldcs_(prev + row);
     T acc = zero_<T>();
     int pos0 = 0;
     for (int k0 = 0; k0 < maxlen; k0 += U) {
@@ -170,15 +158,71 @@ spmv_sell_kernel(SellDevice<T> S, const T* __restrict__ x, T* y, real_t<T> coef,
       if (is_long) {                       // produced by spmv_long_kernel (earlier launch), epilogue included
         if (final_mode) nrm += (double)abs2_(y[row]);
       } else {
-        if (acc_mode) acc = acc + y[row];
+        if (acc_mode) acc = acc + y_in;
         if (final_mode) {
-          if (prev != nullptr) acc = acc + coef * ldcs_(prev + row);
+          if (prev != nullptr) acc = acc + coef * p_in;
           nrm += (double)abs2_(acc);
         }
         y[row] = acc;
       }
     }
     lenb = lenb_n; base = base_n;
+  }
+}
+
+// row-sharded run: the slices of the ranks in src_mask must have landed (epoch `epoch`) before x is gathered.
+// Called by every thread of the CTA (contains a barrier).
+__device__ __forceinline__ void sell_wait_sources(const unsigned long long* flags, unsigned int src_mask, unsigned long long epoch,
+                                                  const ReduceWs& ws) {
+  if (src_mask == 0u) return;
+  if (threadIdx.x < 32 && ((src_mask >> threadIdx.x) & 1u)) {
+    const long long t0 = clock64();
+    while (*reinterpret_cast<const volatile unsigned long long*>(flags + threadIdx.x) < epoch) {
+      if (clock64() - t0 > ws.timeout_cycles) { *ws.host_err = 1u; break; }   // a peer died; do not hang the GPU
+    }
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+// U = independent (ci -> x) gather chains per lane per batch; MINB = CTAs per SM the register budget is capped for
+// (U = 8: <= 51 registers, 5 CTAs = 40 warps per SM; U = 4: <= 32 registers, 8 CTAs = 64 warps per SM)
+template <class T, bool CONJ, int U, int MINB>
+__global__ void __launch_bounds__(kThreads, MINB)
+spmv_sell_kernel(SellDevice<T> S, const T* __restrict__ x, T* y, real_t<T> coef, const T* __restrict__ prev, ReduceWs ws,
+                 int want_norm, int mode, const unsigned long long* flags, unsigned int src_mask, unsigned long long epoch) {
+  __shared__ double red[32];
+  const int lane = threadIdx.x & 31;
+  const unsigned below = (1u << lane) - 1u;
+  sell_wait_sources(flags, src_mask, epoch, ws);
+  const int wid = blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
+  double nrm = 0.0;
+  sell_range<T, CONJ, U>(S, __ldg(S.wstart + wid), __ldg(S.wstart + wid + 1), x, y, coef, prev, (mode & kSellAcc) != 0,
+                         (mode & kSellFinal) != 0, lane, below, nrm);
+  if (want_norm) {
+    double tot = block_sum(nrm, red);
+    grid_publish(tot, 0.0, ws, 1, red);
+  }
+}
+
+// All panels of a split product in ONE launch (row-sharded runs): y = sum_g A_g x + coef*prev, ||y||.  Every warp keeps the
+// same slices in every panel (P.wstart: one partition planned on the un-split operand), so a row is only ever touched by
+// one thread and the panels need no grid-wide ordering: a warp that has finished its share of panel g polls the arrival
+// flags of panel g+1's sources and carries on, while the other warps and the NVLink transfer are still busy.  Compared
+// with one launch per panel this removes G-1 launch gaps, ramps and tails per product (~14.5 us each, measured on 8 GPUs).
+template <class T, bool CONJ, int U, int MINB>
+__global__ void __launch_bounds__(kThreads, MINB)
+spmv_sell_fused_kernel(SellPanelPack<T> P, const T* __restrict__ x, T* y, real_t<T> coef, const T* __restrict__ prev, ReduceWs ws,
+                       int want_norm, const unsigned long long* flags, unsigned long long epoch) {
+  __shared__ double red[32];
+  const int lane = threadIdx.x & 31;
+  const unsigned below = (1u << lane) - 1u;
+  const int wid = blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
+  const long s0 = __ldg(P.wstart + wid), s1 = __ldg(P.wstart + wid + 1);
+  double nrm = 0.0;
+  for (int g = 0; g < P.G; ++g) {
+    if (flags != nullptr) sell_wait_sources(flags, P.mask[g], epoch, ws);
+    sell_range<T, CONJ, U>(P.S[g], s0, s1, x, y, coef, prev, g > 0, g + 1 == P.G, lane, below, nrm);
   }
   if (want_norm) {
     double tot = block_sum(nrm, red);
@@ -190,14 +234,11 @@ spmv_sell_kernel(SellDevice<T> S, const T* __restrict__ x, T* y, real_t<T> coef,
 // best on configs 2 and 5: 32 warps x 8 gather chains beat more warps with spills or shorter batches), 2 (U = 4, 8 CTAs/SM),
 // 3 (U = 12, 3 CTAs/SM), 4 (U = 16, 2 CTAs/SM).  Measured (us, configs 5 / 2 / 4, A x and A^H x): variant 1: 534 588 / 68 68 / 272 136;
 // variant 0: 621 652 / 74 73; variant 2: 778 798 / 88 89 / 394 209; variant 3: 570 587 / 71 72 / 306 154; variant 4: 771 793 / 79 78 / 416 243.
-template <class T> int sell_variant() {
-  static const int v = [] {
-    const char* e = std::getenv("PROPACK_B200_SELL_VARIANT");
-    const int d = 1;
-    const int u = e ? std::atoi(e) : d;
-    return (u < 0 || u > 4) ? d : u;
-  }();
-  return v;
+template <class T> int sell_variant() {   // read at every call: cheap, and lets one process compare settings
+  const char* e = std::getenv("PROPACK_B200_SELL_VARIANT");
+  const int d = 1;
+  const int u = e ? std::atoi(e) : d;
+  return (u < 0 || u > 4) ? d : u;
 }
 template <class T, int V> struct SellCfg;
 template <class T> struct SellCfg<T, 0> { static constexpr int U = 8, MINB = 5; };
@@ -234,6 +275,18 @@ template <class T> int sell_occupancy() {
     default: PB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, spmv_sell_kernel<T, false, SellCfg<T, 2>::U, SellCfg<T, 2>::MINB>, kThreads, 0)); break;
   }
   return std::max(1, occ);
+}
+
+template <class T> int sell_registers() {
+  cudaFuncAttributes a{};
+  switch (sell_variant<T>()) {
+    case 0: PB_CUDA(cudaFuncGetAttributes(&a, spmv_sell_kernel<T, false, SellCfg<T, 0>::U, SellCfg<T, 0>::MINB>)); break;
+    case 1: PB_CUDA(cudaFuncGetAttributes(&a, spmv_sell_kernel<T, false, SellCfg<T, 1>::U, SellCfg<T, 1>::MINB>)); break;
+    case 3: PB_CUDA(cudaFuncGetAttributes(&a, spmv_sell_kernel<T, false, SellCfg<T, 3>::U, SellCfg<T, 3>::MINB>)); break;
+    case 4: PB_CUDA(cudaFuncGetAttributes(&a, spmv_sell_kernel<T, false, SellCfg<T, 4>::U, SellCfg<T, 4>::MINB>)); break;
+    default: PB_CUDA(cudaFuncGetAttributes(&a, spmv_sell_kernel<T, false, SellCfg<T, 2>::U, SellCfg<T, 2>::MINB>)); break;
+  }
+  return a.numRegs;
 }
 
 // -----------------------------------------------------------------------------------------------------------
@@ -321,7 +374,13 @@ void sell_build(Context& c, int rows, int cols, long nnz, const int* rp, const i
   D.len8 = out.len8.p; D.joff = out.joff.p;
   // ctas_per_sm <= 0: every resident slot but -ctas_per_sm (row-sharded operands keep one free for the NVLink push kernel)
   const int occ = sell_occupancy<T>();
-  const int per_sm = ctas_per_sm > 0 ? std::min(ctas_per_sm, occ) : std::max(1, occ + ctas_per_sm);
+  int per_sm = ctas_per_sm > 0 ? std::min(ctas_per_sm, occ) : std::max(1, occ + ctas_per_sm);
+  if (ctas_per_sm <= 0) {
+    // room for the push kernel means registers too: it runs 256 threads x up to 64 registers (level1.cu), and a slot freed
+    // by a 32-register SpMV variant would not hold it
+    const int regs = sell_registers<T>();
+    if (regs > 0) per_sm = std::max(1, std::min(per_sm, (65536 - 64 * kThreads) / (regs * kThreads)));
+  }
   D.grid = c.grid_for(std::max<long>(nslices, 1), kThreads / 32, per_sm);
   const int nwarps = D.grid * (kThreads / 32);
   out.wstart.alloc((size_t)nwarps + 1);
@@ -358,6 +417,53 @@ void sell_build(Context& c, int rows, int cols, long nnz, const int* rp, const i
   c.sync();
 }
 
+void sell_plan_partition(Context& c, int rows, const int* rp, int grid, DeviceBuffer<int>& wstart) {
+  const long nslices = ((long)rows + 31) / 32;
+  const int nwarps = grid * (kThreads / 32);
+  wstart.alloc((size_t)nwarps + 1);
+  if (nslices == 0) { PB_CUDA(cudaMemsetAsync(wstart.p, 0, sizeof(int) * ((size_t)nwarps + 1), c.stream)); c.sync(); return; }
+  DeviceBuffer<long long> count((size_t)nslices + 1), weight((size_t)nslices + 1), wpre((size_t)nslices + 1);
+  DeviceBuffer<unsigned char> len8((size_t)std::max(rows, 1));
+  PB_CUDA(cudaMemsetAsync(weight.p + nslices, 0, sizeof(long long), c.stream));
+  sell_lengths_kernel<<<c.grid_for(nslices, kThreads / 32, 8), kThreads, 0, c.stream>>>(rows, nslices, rp, len8.p, count.p, weight.p);
+  PB_LAUNCH_CHECK();
+  size_t tmp_bytes = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, weight.p, wpre.p, (int)(nslices + 1), c.stream);
+  DeviceBuffer<char> tmp(tmp_bytes + 16);
+  PB_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tmp_bytes, weight.p, wpre.p, (int)(nslices + 1), c.stream));
+  sell_partition_kernel<<<ceil_div(nwarps + 1, kThreads), kThreads, 0, c.stream>>>(nslices, wpre.p, nwarps, wstart.p);
+  PB_LAUNCH_CHECK();
+  c.sync();
+}
+
+template <class T> bool sell_fused_fits(Context& c, int grid) {
+  if (sell_variant<T>() != 1) return false;   // the single-launch kernel exists in the default shape only
+  int occ = 0;
+  PB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, spmv_sell_fused_kernel<T, false, SellCfg<T, 1>::U, SellCfg<T, 1>::MINB>, kThreads, 0));
+  cudaFuncAttributes a{};
+  PB_CUDA(cudaFuncGetAttributes(&a, spmv_sell_fused_kernel<T, false, SellCfg<T, 1>::U, SellCfg<T, 1>::MINB>));
+  const int by_regs = a.numRegs > 0 ? (65536 - 64 * kThreads) / (a.numRegs * kThreads) : 0;   // leave the push kernel its registers
+  return grid <= std::min(occ - 1, by_regs) * c.num_sms;
+}
+
+template <class T>
+void k_spmv_sell_fused(Context& c, const SellPanelPack<T>& P, bool conj, const T* x, T* y, real_t<T> coef, const T* prev, Pending* nrm,
+                       const unsigned long long* flags, unsigned long long epoch) {
+  ReduceWs ws{};
+  int want = 0;
+  if (nrm) { ws = c.new_reduce(nrm); want = 1; }
+  ws.host_err = c.host_err_dev;
+  ws.timeout_cycles = c.peer_timeout_cycles;
+  constexpr int U = SellCfg<T, 1>::U, MINB = SellCfg<T, 1>::MINB;
+  if (conj && scalar_traits<T>::is_complex)
+    spmv_sell_fused_kernel<T, true, U, MINB><<<P.grid, kThreads, 0, c.stream>>>(P, x, y, coef, prev, ws, want, flags, epoch);
+  else
+    spmv_sell_fused_kernel<T, false, U, MINB><<<P.grid, kThreads, 0, c.stream>>>(P, x, y, coef, prev, ws, want, flags, epoch);
+  PB_LAUNCH_CHECK();
+  c.ctr.launches += 1;
+  if (want) c.complete_reduce(*nrm, 1);
+}
+
 template <class T>
 void k_spmv_sell(Context& c, const SellDevice<T>& S, const CsrDevice<T>* long_src, bool conj, const T* x, T* y, real_t<T> coef,
                  const T* prev, Pending* nrm, int mode, const unsigned long long* flags, unsigned int src_mask,
@@ -379,6 +485,9 @@ void k_spmv_sell(Context& c, const SellDevice<T>& S, const CsrDevice<T>* long_sr
 
 #define PB_INST(T)                                                                                                       \
   template void sell_build<T>(Context&, int, int, long, const int*, const int*, const T*, SellStorage<T>&, int);         \
+  template bool sell_fused_fits<T>(Context&, int);                                                                       \
+  template void k_spmv_sell_fused<T>(Context&, const SellPanelPack<T>&, bool, const T*, T*, real_t<T>, const T*, Pending*, \
+                                     const unsigned long long*, unsigned long long);                                     \
   template void k_spmv_sell<T>(Context&, const SellDevice<T>&, const CsrDevice<T>*, bool, const T*, T*, real_t<T>,       \
                                const T*, Pending*, int, const unsigned long long*, unsigned int, unsigned long long);
 PB_INST(float)

@@ -33,6 +33,9 @@ for st in settings:
     kv = dict(x.split("=") for x in st.split(","))
     os.environ["PROPACK_B200_SPMV_PHASES"] = kv.get("PHASES", "4")
     os.environ["PROPACK_B200_PUSH_CTAS"] = kv.get("PUSH", "32")
+    os.environ["PROPACK_B200_PUSH_DEPTH"] = kv.get("DEPTH", "4")      # 128-bit packs in flight per thread of the push kernel
+    os.environ["PROPACK_B200_SELL_VARIANT"] = kv.get("VARIANT", "1")  # SELL kernel shape (sell.cu): 1 = 8 chains x 32 warps/SM, 2 = 4 chains x 64 warps/SM, ...
+    os.environ["PROPACK_B200_SPMV_FUSED_PHASES"] = kv.get("FUSED", "1")   # 1: all phases of a product in one launch (default), 0: one launch per phase
     os.environ["PROPACK_B200_PUSH"] = kv.get("MODE", "ce")            # ce (copy engines, default) | sm (push kernel)
     os.environ["PROPACK_B200_PUSH_CHAINS"] = kv.get("CHAINS", "2")    # concurrent chains of peer copies in the push graph
     os.environ["PROPACK_B200_PUSH_GRAPH"] = kv.get("GRAPH", "1")      # 0: plain stream-ordered copies instead of the CUDA graph
@@ -58,8 +61,18 @@ for st in settings:
     pms, _, _, _, _ = solve()
     ph = {kname: round(v["ms"], 1) for kname, v in propack_b200.phase_ms().items()}
     propack_b200.set_profile(False)
+    # the local panel launches alone (no all-gather, whatever the gather buffer holds) and the un-staged product (NCCL all-gather +
+    # panels), both directions, CUDA events, L2 flushed: what the transport has to hide
+    iso = {}
+    for skip in (1, 0):
+        L.propack_b200_set_option(b"bench_skip_gather", C.c_int(skip))
+        for adj in (0, 1):
+            dist.barrier()
+            t_ms = L.propack_b200_bench_spmv(C.c_int(op.handle), C.c_int(adj), C.c_int(10), C.c_int(1))
+            iso[("local_panels" if skip else "nccl_gather+panels") + ("_t" if adj else "_n") + "_us"] = round(1e3 * t_ms, 1)
+    L.propack_b200_set_option(b"bench_skip_gather", C.c_int(0))
     if rank == 0:
-        print(json.dumps({"workload": wl, "world": world, "setting": st, "ms": ts, "steps": ctr["nsteps"], "converged": kc, "info": info,
+        print(json.dumps({"workload": wl, "spmv_isolated": iso, "world": world, "setting": st, "ms": ts, "steps": ctr["nsteps"], "converged": kc, "info": info,
                           "sigma_1": float(sigma[0]) if kc else None, "profiled_ms": round(pms, 1), "phases_ms": ph}), flush=True)
     sv.close(); op.close()
 pdist.finalize_comm()
