@@ -119,10 +119,6 @@ template <class T> struct PanelSet {
   std::vector<std::unique_ptr<Panel>> panels;
   long nnz = 0;
   int rows = 0;
-  // row-sharded operands: all panels in one launch (sell.cu: spmv_sell_fused_kernel) when no panel has long rows and the
-  // kernel fits beside the push kernel; PROPACK_B200_SPMV_FUSED_PHASES=0 keeps one launch per panel
-  SellPanelPack<T> pack;
-  DeviceBuffer<int> pack_wstart;
   // Split the CSR (device pointers) into G panels: panel of column c = ring distance of (c / ld) behind `rank`, / (P/G).
   // Returns the validation status of k_csr_split_phases (0 = ok).
   int build(Context& c, int rows_, long width, long nnz_, const int* rp, const int* ci, const T* va, long ld, int P, int rank, int G,
@@ -156,29 +152,12 @@ template <class T> struct PanelSet {
           if (src != rank) pn.src_mask |= 1u << src;
         }
     }
-    pack = SellPanelPack<T>();
-    const char* e = std::getenv("PROPACK_B200_SPMV_FUSED_PHASES");
-    if (P > 1 && G > 1 && G <= kSellMaxPanels && spmv_use_sell() && !(e && e[0] == '0')) {
-      bool ok = sell_fused_fits<T>(c, panels[0]->S.sell.dev.grid);
-      for (int g = 0; g < G; ++g) ok = ok && panels[g]->S.csr.n_long == 0 && panels[g]->S.sell.dev.grid == panels[0]->S.sell.dev.grid;
-      if (ok) {
-        pack.G = G;
-        pack.grid = panels[0]->S.sell.dev.grid;
-        sell_plan_partition(c, rows, rp, pack.grid, pack_wstart);
-        pack.wstart = pack_wstart.p;
-        for (int g = 0; g < G; ++g) { pack.S[g] = panels[g]->S.sell.dev; pack.mask[g] = panels[g]->src_mask; }
-      }
-    }
     return 0;
   }
   // y = sum_g A_g x + coef*prev, ||y||.  flags != null: panel g first waits for the arrival flags of its sources.
   void apply(Context& c, bool conj, const T* x, T* y, R coef, const T* prev, Pending* nrm, const unsigned long long* flags,
              unsigned long long epoch) {
     const size_t G = panels.size();
-    if (pack.G > 0 && flags != nullptr) {   // staged row-sharded product: one launch, the panels wait for their sources in-kernel
-      k_spmv_sell_fused<T>(c, pack, conj, x, y, coef, prev, nrm, flags, epoch);
-      return;
-    }
     for (size_t g = 0; g < G; ++g) {
       Panel& pn = *panels[g];
       const unsigned int mask = flags ? pn.src_mask : 0u;
@@ -269,7 +248,9 @@ template <class T> struct ShardedCsrOperator : LinOp<T> {
     for (int d = 0; d < 2; ++d) if (push_graph[d]) cudaGraphExecDestroy(push_graph[d]);
   }
   // ---- transport of the fused all-gather ------------------------------------------------------------------------
-  // Default: the COPY ENGINES move the slice (PROPACK_B200_PUSH=sm selects the SM-store push kernel of k_scal_push).
+  // Default: the SM-store push kernel of k_scal_push (64 thin CTAs on the side stream).  PROPACK_B200_PUSH=ce moves the
+  // slices with the COPY ENGINES instead (measured on 8 GPUs, config 5: 982-1042 ms against 937-954 ms -- a dependent chain
+  // of 10 MB peer copies pays ~6 us of engine start-up per copy; kept as the transport that needs no SM at all).
   // One CUDA graph per direction, built once: for every destination at ring distance k = 1..P-1 a peer memcpy of this
   // rank's slice (own gather slot -> the same slot of the destination's window) followed by an 8-byte copy of the epoch
   // word into the destination's arrival flag -- stream order makes the flag land after the data.  The destinations are
@@ -279,7 +260,7 @@ template <class T> struct ShardedCsrOperator : LinOp<T> {
   const int push_chains = [] { const char* e = std::getenv("PROPACK_B200_PUSH_CHAINS"); const int v = e ? std::atoi(e) : 2; return std::min(7, std::max(1, v)); }();
   cudaGraphExec_t push_graph[2] = {nullptr, nullptr};
   DeviceBuffer<unsigned long long> epoch_dev;
-  const bool ce_push = [] { const char* e = std::getenv("PROPACK_B200_PUSH"); return !(e && (e[0] == 's' || e[0] == 'S')); }();   // per operator
+  const bool ce_push = [] { const char* e = std::getenv("PROPACK_B200_PUSH"); return e && (e[0] == 'c' || e[0] == 'C'); }();   // per operator
   bool push_by_copy_engine() const { return ce_push; }
   bool graph_unavailable = [] { const char* e = std::getenv("PROPACK_B200_PUSH_GRAPH"); return e && e[0] == '0'; }();
   // the same copies issued one by one on the side stream (one chain): used when the graph cannot be built

@@ -86,15 +86,6 @@ template <class T> struct SellDevice {
   const int* wstart = nullptr;        // [grid*8 + 1]
   int grid = 0;                       // CTAs the partition was made for (the kernel is launched with exactly this grid)
 };
-// the panels of one split product, for the single-launch kernel of row-sharded runs (sell.cu: spmv_sell_fused_kernel)
-constexpr int kSellMaxPanels = 8;
-template <class T> struct SellPanelPack {
-  int G = 0;
-  SellDevice<T> S[kSellMaxPanels];
-  unsigned int mask[kSellMaxPanels] = {0, 0, 0, 0, 0, 0, 0, 0};   // source ranks whose arrival flags panel g waits for
-  const int* wstart = nullptr;        // [grid*8 + 1] ONE warp partition for all panels (planned on the un-split operand)
-  int grid = 0;
-};
 template <class T> struct SellStorage {
   DeviceBuffer<long long> joff;
   DeviceBuffer<unsigned char> len8;
@@ -113,14 +104,6 @@ void sell_build(Context& c, int rows, int cols, long nnz, const int* rp, const i
 // flags/src_mask/epoch: row-sharded runs -- wait in-kernel until the gather-buffer slices of the ranks in src_mask
 // have arrived (flags[r] >= epoch); src_mask = 0: no wait.
 constexpr int kSellModeAcc = 1, kSellModeFinal = 2;
-// One warp partition of the 32-row slices of a CSR operand (weights as in sell_build) for a grid of `grid` CTAs.
-void sell_plan_partition(Context& c, int rows, const int* rp, int grid, DeviceBuffer<int>& wstart);
-// true when the single-launch kernel can run `grid` CTAs co-resident and still leave the push kernel its slot
-template <class T> bool sell_fused_fits(Context& c, int grid);
-// y = sum_g A_g x + coef*prev, ||y||: all panels in one launch; flags != null: panel g first waits for P.mask[g]'s arrival flags
-template <class T>
-void k_spmv_sell_fused(Context& c, const SellPanelPack<T>& P, bool conj, const T* x, T* y, real_t<T> coef, const T* prev, Pending* nrm,
-                       const unsigned long long* flags, unsigned long long epoch);
 template <class T>
 void k_spmv_sell(Context& c, const SellDevice<T>& S, const CsrDevice<T>* long_src, bool conj, const T* x, T* y, real_t<T> coef,
                  const T* prev, Pending* nrm, int mode, const unsigned long long* flags, unsigned int src_mask,

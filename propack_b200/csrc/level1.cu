@@ -226,7 +226,7 @@ template <class T> void k_scal(Context& c, long n, T* x, real_t<T> a) {
 }
 inline int push_ctas() {   // read at every call: cheap, and lets one process compare settings
   const char* e = std::getenv("PROPACK_B200_PUSH_CTAS");
-  const int v = e ? std::atoi(e) : 32;
+  const int v = e ? std::atoi(e) : 64;   // measured on 8 GPUs, config 5: 32 -> 1050 ms, 48/64 -> 954-977, 96 -> 990, 128/148 -> 1005 (pre y-prefetch)
   return std::min(148, std::max(1, v));
 }
 inline int push_depth() {

@@ -205,31 +205,6 @@ spmv_sell_kernel(SellDevice<T> S, const T* __restrict__ x, T* y, real_t<T> coef,
   }
 }
 
-// All panels of a split product in ONE launch (row-sharded runs): y = sum_g A_g x + coef*prev, ||y||.  Every warp keeps the
-// same slices in every panel (P.wstart: one partition planned on the un-split operand), so a row is only ever touched by
-// one thread and the panels need no grid-wide ordering: a warp that has finished its share of panel g polls the arrival
-// flags of panel g+1's sources and carries on, while the other warps and the NVLink transfer are still busy.  Compared
-// with one launch per panel this removes G-1 launch gaps, ramps and tails per product (~14.5 us each, measured on 8 GPUs).
-template <class T, bool CONJ, int U, int MINB>
-__global__ void __launch_bounds__(kThreads, MINB)
-spmv_sell_fused_kernel(SellPanelPack<T> P, const T* __restrict__ x, T* y, real_t<T> coef, const T* __restrict__ prev, ReduceWs ws,
-                       int want_norm, const unsigned long long* flags, unsigned long long epoch) {
-  __shared__ double red[32];
-  const int lane = threadIdx.x & 31;
-  const unsigned below = (1u << lane) - 1u;
-  const int wid = blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
-  const long s0 = __ldg(P.wstart + wid), s1 = __ldg(P.wstart + wid + 1);
-  double nrm = 0.0;
-  for (int g = 0; g < P.G; ++g) {
-    if (flags != nullptr) sell_wait_sources(flags, P.mask[g], epoch, ws);
-    sell_range<T, CONJ, U>(P.S[g], s0, s1, x, y, coef, prev, g > 0, g + 1 == P.G, lane, below, nrm);
-  }
-  if (want_norm) {
-    double tot = block_sum(nrm, red);
-    grid_publish(tot, 0.0, ws, 1, red);
-  }
-}
-
 // kernel variant: PROPACK_B200_SELL_VARIANT = 0 (U = 8, 5 CTAs/SM), 1 (U = 8, 4 CTAs/SM: no register cap; the default -- measured
 // best on configs 2 and 5: 32 warps x 8 gather chains beat more warps with spills or shorter batches), 2 (U = 4, 8 CTAs/SM),
 // 3 (U = 12, 3 CTAs/SM), 4 (U = 16, 2 CTAs/SM).  Measured (us, configs 5 / 2 / 4, A x and A^H x): variant 1: 534 588 / 68 68 / 272 136;
@@ -375,7 +350,7 @@ void sell_build(Context& c, int rows, int cols, long nnz, const int* rp, const i
   // ctas_per_sm <= 0: every resident slot but -ctas_per_sm (row-sharded operands keep one free for the NVLink push kernel)
   const int occ = sell_occupancy<T>();
   int per_sm = ctas_per_sm > 0 ? std::min(ctas_per_sm, occ) : std::max(1, occ + ctas_per_sm);
-  if (ctas_per_sm <= 0) {
+  if (ctas_per_sm < 0) {
     // room for the push kernel means registers too: it runs 256 threads x up to 64 registers (level1.cu), and a slot freed
     // by a 32-register SpMV variant would not hold it
     const int regs = sell_registers<T>();
@@ -417,53 +392,6 @@ void sell_build(Context& c, int rows, int cols, long nnz, const int* rp, const i
   c.sync();
 }
 
-void sell_plan_partition(Context& c, int rows, const int* rp, int grid, DeviceBuffer<int>& wstart) {
-  const long nslices = ((long)rows + 31) / 32;
-  const int nwarps = grid * (kThreads / 32);
-  wstart.alloc((size_t)nwarps + 1);
-  if (nslices == 0) { PB_CUDA(cudaMemsetAsync(wstart.p, 0, sizeof(int) * ((size_t)nwarps + 1), c.stream)); c.sync(); return; }
-  DeviceBuffer<long long> count((size_t)nslices + 1), weight((size_t)nslices + 1), wpre((size_t)nslices + 1);
-  DeviceBuffer<unsigned char> len8((size_t)std::max(rows, 1));
-  PB_CUDA(cudaMemsetAsync(weight.p + nslices, 0, sizeof(long long), c.stream));
-  sell_lengths_kernel<<<c.grid_for(nslices, kThreads / 32, 8), kThreads, 0, c.stream>>>(rows, nslices, rp, len8.p, count.p, weight.p);
-  PB_LAUNCH_CHECK();
-  size_t tmp_bytes = 0;
-  cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, weight.p, wpre.p, (int)(nslices + 1), c.stream);
-  DeviceBuffer<char> tmp(tmp_bytes + 16);
-  PB_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tmp_bytes, weight.p, wpre.p, (int)(nslices + 1), c.stream));
-  sell_partition_kernel<<<ceil_div(nwarps + 1, kThreads), kThreads, 0, c.stream>>>(nslices, wpre.p, nwarps, wstart.p);
-  PB_LAUNCH_CHECK();
-  c.sync();
-}
-
-template <class T> bool sell_fused_fits(Context& c, int grid) {
-  if (sell_variant<T>() != 1) return false;   // the single-launch kernel exists in the default shape only
-  int occ = 0;
-  PB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, spmv_sell_fused_kernel<T, false, SellCfg<T, 1>::U, SellCfg<T, 1>::MINB>, kThreads, 0));
-  cudaFuncAttributes a{};
-  PB_CUDA(cudaFuncGetAttributes(&a, spmv_sell_fused_kernel<T, false, SellCfg<T, 1>::U, SellCfg<T, 1>::MINB>));
-  const int by_regs = a.numRegs > 0 ? (65536 - 64 * kThreads) / (a.numRegs * kThreads) : 0;   // leave the push kernel its registers
-  return grid <= std::min(occ - 1, by_regs) * c.num_sms;
-}
-
-template <class T>
-void k_spmv_sell_fused(Context& c, const SellPanelPack<T>& P, bool conj, const T* x, T* y, real_t<T> coef, const T* prev, Pending* nrm,
-                       const unsigned long long* flags, unsigned long long epoch) {
-  ReduceWs ws{};
-  int want = 0;
-  if (nrm) { ws = c.new_reduce(nrm); want = 1; }
-  ws.host_err = c.host_err_dev;
-  ws.timeout_cycles = c.peer_timeout_cycles;
-  constexpr int U = SellCfg<T, 1>::U, MINB = SellCfg<T, 1>::MINB;
-  if (conj && scalar_traits<T>::is_complex)
-    spmv_sell_fused_kernel<T, true, U, MINB><<<P.grid, kThreads, 0, c.stream>>>(P, x, y, coef, prev, ws, want, flags, epoch);
-  else
-    spmv_sell_fused_kernel<T, false, U, MINB><<<P.grid, kThreads, 0, c.stream>>>(P, x, y, coef, prev, ws, want, flags, epoch);
-  PB_LAUNCH_CHECK();
-  c.ctr.launches += 1;
-  if (want) c.complete_reduce(*nrm, 1);
-}
-
 template <class T>
 void k_spmv_sell(Context& c, const SellDevice<T>& S, const CsrDevice<T>* long_src, bool conj, const T* x, T* y, real_t<T> coef,
                  const T* prev, Pending* nrm, int mode, const unsigned long long* flags, unsigned int src_mask,
@@ -485,9 +413,6 @@ void k_spmv_sell(Context& c, const SellDevice<T>& S, const CsrDevice<T>* long_sr
 
 #define PB_INST(T)                                                                                                       \
   template void sell_build<T>(Context&, int, int, long, const int*, const int*, const T*, SellStorage<T>&, int);         \
-  template bool sell_fused_fits<T>(Context&, int);                                                                       \
-  template void k_spmv_sell_fused<T>(Context&, const SellPanelPack<T>&, bool, const T*, T*, real_t<T>, const T*, Pending*, \
-                                     const unsigned long long*, unsigned long long);                                     \
   template void k_spmv_sell<T>(Context&, const SellDevice<T>&, const CsrDevice<T>*, bool, const T*, T*, real_t<T>,       \
                                const T*, Pending*, int, const unsigned long long*, unsigned int, unsigned long long);
 PB_INST(float)

@@ -10,7 +10,7 @@ PROPACK_B200_GEMM_MT2=1 PROF_NO_SPMV=1 PROF_LS=300 timeout 300 python tools/prof
 PROPACK_B200_GEMM_MT2=1 timeout 600 python -m pytest tests/test_gpu_kernels.py -m gpu -q --timeout 600 -p no:cacheprovider -k "gemm or ritzvec" > $O/r02_pytest_gemm_mt2.log 2>&1; tail -2 $O/r02_pytest_gemm_mt2.log
 PROF_NO_SPMV=1 PROF_REPS=1 PROF_LS=300 timeout 900 ncu --set full --clock-control none --import-source on -k regex:'gemv_t_tma_kernel|gemv_n_kernel|gemm_tall' -c 16 -o $O/r02_prof_gemv_gemm -f python tools/prof_target.py c5 > $O/r02_ncu_gemv_gemm.log 2>&1
 tail -2 $O/r02_ncu_gemv_gemm.log
-timeout 600 python tools/spmv_micro.py banded > $O/r02_spmv_banded.json 2> $O/r02_spmv_banded.err; cat $O/r02_spmv_banded.json
+timeout 600 python tools/spmv_micro.py banded:4000000 > $O/r02_spmv_banded.json 2> $O/r02_spmv_banded.err; cat $O/r02_spmv_banded.json
 timeout 1700 python -m pytest tests -m gpu -q --timeout 900 -p no:cacheprovider > $O/r02_pytest_gpu_full.log 2>&1; echo "rc=$?" >> $O/r02_pytest_gpu_full.log; tail -6 $O/r02_pytest_gpu_full.log
 timeout 1500 python bench.py --steps 3 --warmup 3 > $O/r02_bench_c5_n1_final.json 2> $O/r02_bench_c5_n1_final.err; echo "bench c5 rc=$?"
 python - <<'P'
@@ -21,6 +21,6 @@ try:
     print(d['e2e']); print({k:d['roofline'][k] for k in ('kernel','achieved','frac','share_of_solve','traffic')})
 except Exception as e: print('bench c5 parse failed', e)
 P
-timeout 600 python bench.py --workload c2 --steps 5 --warmup 3 --no-cpu-baseline > $O/r02_bench_c2_n1_final.json 2> $O/r02_bench_c2_n1_final.err
+timeout 600 python bench.py --workload c2 --steps 3 --warmup 3 --no-cpu-baseline > $O/r02_bench_c2_n1_final.json 2> $O/r02_bench_c2_n1_final.err
 python -c "
 import json; d=json.load(open('gpurun_out/r02_bench_c2_n1_final.json')); print(d['ms_per_step'], d['e2e'])"
