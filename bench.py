@@ -59,11 +59,11 @@ IRL_MAXITER = 50
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel at working size, from the committed
 # `ncu --set full` captures (profiles/r02_ncu_extract.txt); filled in by hand from those files, None = not captured
 # (SpMV: per product = the 2 column-panel launches of spmv_sell_kernel on config 5, mean of A x and A^T u; reorth: one GEMV
-# pair gemv_t_tma_kernel + gemv_n_kernel at L = 1e7, l = 64 -- 10.485 GB against 10.48 GB algorithmic)
-NCU_TRAFFIC_BYTES_PER_LAUNCH = {("c5", "spmv"): 1.676e9, ("c5", "reorth"): 10.485e9, ("c2", "spmv"): 140.03e6 + 5.3e6, ("c2", "reorth"): None}
+# pair gemv_t_tma_kernel + gemv_n_kernel at L = 1e7, l = 300 -- 48.27 GB against 48.24 GB algorithmic)
+NCU_TRAFFIC_BYTES_PER_LAUNCH = {("c5", "spmv"): 1.676e9, ("c5", "reorth"): 48.27e9, ("c2", "spmv"): 140.03e6 + 5.3e6, ("c2", "reorth"): None}
 NCU_TRAFFIC_NOTE = {("c5", "spmv"): "dram__bytes_read+write of the 2 panel launches of one product (profiles/r02_ncu_extract_c5.txt [0]+[1] / [6]+[7]); "
                                     "algorithmic 1.48 GB + the second panel's read-modify-write of y (0.16 GB)",
-                    ("c5", "reorth"): "one GEMV pair at L=1e7, l=64 (profiles/r02_ncu_extract_c5.txt [12]+[13]): 10.485 GB measured vs 10.48 GB algorithmic"}
+                    ("c5", "reorth"): "one GEMV pair at L=1e7, l=300 (profiles/r02_ncu_extract_gemv_gemm.txt [4]+[5]): 48.27 GB measured vs 48.24 GB algorithmic"}
 CPU_SAMPLE_STEPS = 150  # Lanczos steps of the same problem the in-line cpu_baseline runs (bounded sample, ~10-30 s)
 REF_BUDGET_S = 500.0    # --impl reference: stop adding full CPU solves once the projected run time passes this
 SCIPY_START_BEFORE_S = 400.0   # ... and only start the SciPy cross-check (~4 min on config 5's 1/10 replica) this early in the run
@@ -637,9 +637,10 @@ def run_ours_sharded(args):
     # per-phase CUDA-event timers of one extra solve (rank 0's view; adds an event sync per phase, so it is slower than the
     # timed solves; "aprod" includes the wait for the other ranks' slices, "level1" the fused normalise + all-gather push)
     propack_b200.set_profile(True)
-    pms, _, _, _, _ = solve_resident()
+    pms, _roofline_ctr, _, _, _ = solve_resident()
     ph = {kname: v["ms"] for kname, v in propack_b200.phase_ms().items()}
     propack_b200.set_profile(False)
+    _roofline_bytes = (op.bytes_per_product(False), op.bytes_per_product(True))
 
     # e2e: this rank's shard from pinned host memory -> device, solve, its slices of U, V and sigma back to the host
     pin = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a, dtype=dt)).pin_memory().numpy()
@@ -682,9 +683,30 @@ def run_ours_sharded(args):
     d2h = ((rows_b[1] - rows_b[0]) + (cols_b[1] - cols_b[0])) * k * 8 + 2 * k * 8
     nar, nag, agb = C.c_longlong(0), C.c_longlong(0), C.c_double(0)
     L.propack_b200_comm_stats(C.byref(nar), C.byref(nag), C.byref(agb))
+    # roofline of the dominant phase (the products): HBM bytes streamed by all ranks / rank 0's aprod time of the profiled solve, against
+    # N x the measured HBM peak; and the NVLink floor of the all-gather that sits on the same critical path (sparse operator)
+    peak1, peak_src = peaks()
+    w = 8.0
+    try:
+        per_rank = float(_roofline_ctr["nopx"]) / 2.0 * (_roofline_bytes[0] + _roofline_bytes[1])
+        tb = torch.tensor([per_rank], device="cuda", dtype=torch.float64); dist.all_reduce(tb)
+        aprod_ms = ph.get("aprod", 0.0)
+        ach = float(tb.item()) / (aprod_ms * 1e-3) / 1e9 if aprod_ms > 0 else 0.0
+        gather_in = 0.0 if dense else w * (m + n) * (world - 1) / world       # bytes a rank must receive per Lanczos step (two products)
+        roofline = {"bound": "hbm", "kernel": ("dense APROD = gemv_n_kernel / gemv_t_tma_kernel over the local row block" if dense else
+                                               "spmv_sell_kernel, phase-split over the source ranks of the gathered vector (all ranks)"),
+                    "achieved": ach, "peak": peak1 * world, "unit": "GB/s", "frac": ach / (peak1 * world), "peak_source": peak_src + f" x {world} GPUs",
+                    "traffic": None, "algorithmic_bytes": float(tb.item()), "kernel_ms_in_solve": aprod_ms,
+                    "share_of_solve": aprod_ms / max(sum(ph.values()), 1e-9),
+                    "nvlink_floor": None if dense else {"bytes_in_per_rank_per_step": gather_in, "measured_peer_gbs_per_direction": 770.0,
+                                                        "floor_ms_per_solve": gather_in / 770e9 * 1e3 * float(_roofline_ctr["nsteps"]),
+                                                        "note": "the all-gather of the SpMV input is on the critical path of every product "
+                                                                "(SpMV -> all-gather -> SpMV); aprod time includes waiting for the slices"},
+                    "how": "rank 0's CUDA-event phase timers in one extra profiled solve; bytes summed over ranks"}
+    except Exception as e:   # never let the bookkeeping take the bench line down
+        roofline = {"bound": "hbm", "error": repr(e)[:200]}
     if rank == 0:
         ctr, sigma, kc, info = last
-        peak, peak_src = peaks()
         line = {
             "metric": "lanczos_steps_per_s", "value": value, "unit": "steps/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong",
@@ -708,7 +730,7 @@ def run_ours_sharded(args):
                              "session + local U,V slices and sigma copied back; bytes are per rank") if dense else
                             ("per rank: propack_b200_csr_create_sharded_d (pinned host shard) + solver session + local U,V slices and "
                              "sigma copied back; bytes are per rank")},
-            "roofline": None, "phases_ms_profiled_solve": ph, "profiled_solve_ms": pms, "clocks": clk,
+            "roofline": roofline, "phases_ms_profiled_solve": ph, "profiled_solve_ms": pms, "clocks": clk,
         }
         sys.stdout.flush()
         os.dup2(saved_stdout, 1)

@@ -166,9 +166,8 @@ int csr_create_sharded(int mg, int ng, const int* row_rp, const int* row_ci, con
     if (k_csr_check_rowptr(c, rows, nnz, rp.p)) throw std::runtime_error("propack_b200: sharded CSR row pointers must be non-decreasing");
     // one CTA slot per SM stays free, so that the NVLink push kernel of the side stream can always become resident while
     // the SpMV CTAs spin on arrival flags
-    // (the copy-engine transport needs no SM: the SpMV may take every slot; PROPACK_B200_SPMV_RESERVE_SLOT=1 keeps one free anyway)
-    const char* rs = std::getenv("PROPACK_B200_SPMV_RESERVE_SLOT");
-    const bool reserve = !op->push_by_copy_engine() || (rs && rs[0] == '1');
+    // (the copy-engine transport needs no SM: the SpMV may then take every slot)
+    const bool reserve = !op->push_by_copy_engine();
     const int st = op->sets[d].build(c, rows, ld * cm.world, nnz, rp.p, ci.p, va.p, ld, cm.world, cm.rank, G,
                                      reserve ? /*all resident slots but one*/ -1 : /*all resident slots*/ 0);
     if (st & 2) throw std::runtime_error("propack_b200: sharded CSR index out of range");

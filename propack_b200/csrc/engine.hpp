@@ -245,26 +245,20 @@ template <class T> struct ShardedCsrOperator : LinOp<T> {
   }
   ~ShardedCsrOperator() override {
     if (fused) { cudaDeviceSynchronize(); Comm& cm = Comm::get(); cm.free_window(win[0]); cm.free_window(win[1]); }
-    for (int d = 0; d < 2; ++d) if (push_graph[d]) cudaGraphExecDestroy(push_graph[d]);
   }
   // ---- transport of the fused all-gather ------------------------------------------------------------------------
   // Default: the SM-store push kernel of k_scal_push (64 thin CTAs on the side stream).  PROPACK_B200_PUSH=ce moves the
-  // slices with the COPY ENGINES instead (measured on 8 GPUs, config 5: 982-1042 ms against 937-954 ms -- a dependent chain
-  // of 10 MB peer copies pays ~6 us of engine start-up per copy; kept as the transport that needs no SM at all).
-  // One CUDA graph per direction, built once: for every destination at ring distance k = 1..P-1 a peer memcpy of this
-  // rank's slice (own gather slot -> the same slot of the destination's window) followed by an 8-byte copy of the epoch
-  // word into the destination's arrival flag -- stream order makes the flag land after the data.  The destinations are
-  // spread over `push_chains` (default 2, PROPACK_B200_PUSH_CHAINS) chains of dependent copies (k = 1, 1+C, ... on chain 0, ...), so slices arrive in ring order
-  // (what the phase-split SpMV consumes first lands first) while two copies are always in flight to fill the NVLink
-  // egress.  No SM executes a store for the transfer: the SpMV keeps every SM, and NVLink runs at the copy-engine rate.
-  const int push_chains = [] { const char* e = std::getenv("PROPACK_B200_PUSH_CHAINS"); const int v = e ? std::atoi(e) : 2; return std::min(7, std::max(1, v)); }();
-  cudaGraphExec_t push_graph[2] = {nullptr, nullptr};
-  DeviceBuffer<unsigned long long> epoch_dev;
+  // slices with the COPY ENGINES instead: for every destination at ring distance k = 1..P-1 a peer cudaMemcpyAsync of
+  // this rank's slice (own gather slot -> the same slot of the destination's window) followed by an 8-byte copy of the
+  // epoch word into the destination's arrival flag, all on the side stream -- stream order makes the flag land after the
+  // data and the slices arrive in ring order, as the phase-split SpMV expects.  No SM executes a store for the transfer
+  // (the SpMV may then use every CTA slot).  Measured on 8 GPUs, config 5: 982-1000 ms against 937-954 ms for the push
+  // kernel (a dependent chain of 10 MB peer copies pays ~6 us of engine start-up per copy; the same copies as a CUDA
+  // graph with 1 / 2 / 3 parallel chains: 1017 / 1042 / 1102 ms, all at once: 1293 ms), so the push kernel stays the default.
   const bool ce_push = [] { const char* e = std::getenv("PROPACK_B200_PUSH"); return e && (e[0] == 'c' || e[0] == 'C'); }();   // per operator
   bool push_by_copy_engine() const { return ce_push; }
-  bool graph_unavailable = [] { const char* e = std::getenv("PROPACK_B200_PUSH_GRAPH"); return e && e[0] == '0'; }();
-  // the same copies issued one by one on the side stream (one chain): used when the graph cannot be built
-  void push_direct(Context& c, int d, long len) {
+  DeviceBuffer<unsigned long long> epoch_dev;
+  void push_by_copies(Context& c, int d, long len) {
     Comm& cm = Comm::get();
     const long ld = ld_of(d);
     T* self = xfull[d] + (size_t)cm.rank * ld;
@@ -277,38 +271,6 @@ template <class T> struct ShardedCsrOperator : LinOp<T> {
       PB_CUDA(cudaMemcpyAsync(dst_flags + cm.rank, epoch_dev.p + d, sizeof(unsigned long long), cudaMemcpyDeviceToDevice, c.stream2));
     }
   }
-  void build_push_graph(int d, long len) {
-    Comm& cm = Comm::get();
-    if (!epoch_dev.p) { epoch_dev.alloc(2); PB_CUDA(cudaMemset(epoch_dev.p, 0, 2 * sizeof(unsigned long long))); }
-    cudaGraph_t g;
-    PB_CUDA(cudaGraphCreate(&g, 0));
-    const long ld = ld_of(d);
-    T* self = xfull[d] + (size_t)cm.rank * ld;
-    cudaGraphNode_t tail[Comm::kMaxRanks];
-    bool has_tail[Comm::kMaxRanks];
-    for (int i = 0; i < Comm::kMaxRanks; ++i) has_tail[i] = false;
-    for (int k = 1; k < cm.world; ++k) {
-      const int ch = (k - 1) % push_chains;
-      const int dest = (cm.rank + k) % cm.world;
-      T* dst_base = static_cast<T*>(win[d].base[dest]);
-      unsigned long long* dst_flags = reinterpret_cast<unsigned long long*>(dst_base + (size_t)cm.world * ld);
-      cudaGraphNode_t data_node, flag_node;
-      bool have_data = false;
-      if (len > 0) {
-        PB_CUDA(cudaGraphAddMemcpyNode1D(&data_node, g, has_tail[ch] ? &tail[ch] : nullptr, has_tail[ch] ? 1 : 0,
-                                         dst_base + (size_t)cm.rank * ld, self, sizeof(T) * (size_t)len, cudaMemcpyDeviceToDevice));
-        have_data = true;
-      }
-      const cudaGraphNode_t* dep = have_data ? &data_node : (has_tail[ch] ? &tail[ch] : nullptr);
-      PB_CUDA(cudaGraphAddMemcpyNode1D(&flag_node, g, dep, dep ? 1 : 0, dst_flags + cm.rank, epoch_dev.p + d,
-                                       sizeof(unsigned long long), cudaMemcpyDeviceToDevice));
-      // the next slice of this chain starts behind this one's DATA (its flag copy overlaps the next transfer)
-      tail[ch] = have_data ? data_node : flag_node;
-      has_tail[ch] = true;
-    }
-    PB_CUDA(cudaGraphInstantiate(&push_graph[d], g, 0));
-    PB_CUDA(cudaGraphDestroy(g));
-  }
   const unsigned long long* flags(int d) const {
     return reinterpret_cast<const unsigned long long*>(xfull[d] + (size_t)ld_of(d) * Comm::get().world);
   }
@@ -320,16 +282,11 @@ template <class T> struct ShardedCsrOperator : LinOp<T> {
     const long len = adjoint ? this->m : this->n;
     T* self = xfull[d] + (size_t)cm.rank * ld_of(d);
     if (push_by_copy_engine()) {
-      if (!push_graph[d] && !graph_unavailable) {
-        try { build_push_graph(d, len); }
-        catch (const std::exception&) { graph_unavailable = true; (void)cudaGetLastError(); }   // plain stream-ordered copies instead
-      }
       if (!epoch_dev.p) { epoch_dev.alloc(2); PB_CUDA(cudaMemset(epoch_dev.p, 0, 2 * sizeof(unsigned long long))); }
       k_scal_local<T>(c, len, x, scale, self, epoch_dev.p + d, epoch[d]);
       PB_CUDA(cudaEventRecord(c.ev_fork, c.stream));
       PB_CUDA(cudaStreamWaitEvent(c.stream2, c.ev_fork, 0));
-      if (push_graph[d]) PB_CUDA(cudaGraphLaunch(push_graph[d], c.stream2));
-      else push_direct(c, d, len);
+      push_by_copies(c, d, len);
     } else {
       k_scal_push<T>(c, len, ld_of(d), x, scale, win[d].table_dev, cm.rank, cm.world, epoch[d], self);
     }

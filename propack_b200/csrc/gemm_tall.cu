@@ -151,21 +151,15 @@ void launch_slab(Context& c, long Mr, int N, int K, R* A, long lda, const double
   c.ctr.launches += 1;
 }
 
-// PROPACK_B200_GEMM_MT2=1: two m-tiles per warp for the 10- and 13-tile widths (each W fragment feeds two DMMAs; 1 CTA/SM)
-inline bool gemm_mt2() {
-  static const bool on = [] { const char* e = std::getenv("PROPACK_B200_GEMM_MT2"); return e && e[0] == '1'; }();
-  return on;
-}
-
 template <class R>
 void slab(Context& c, int nt, long Mr, int N, int K, R* A, long lda, const double* Wp, int nt_total, int nt0, R* dst, long ldd) {
   if (nt <= 2) launch_slab<R, 2, 4>(c, Mr, N, K, A, lda, Wp, nt_total, nt0, dst, ldd);
   else if (nt <= 4) launch_slab<R, 4, 4>(c, Mr, N, K, A, lda, Wp, nt_total, nt0, dst, ldd);
   else if (nt <= 7) launch_slab<R, 7, 2>(c, Mr, N, K, A, lda, Wp, nt_total, nt0, dst, ldd);
-  else if (nt <= 10) { if (gemm_mt2()) launch_slab<R, 10, 2>(c, Mr, N, K, A, lda, Wp, nt_total, nt0, dst, ldd);
-                       else launch_slab<R, 10, 1>(c, Mr, N, K, A, lda, Wp, nt_total, nt0, dst, ldd); }
-  else if (nt <= 13) { if (gemm_mt2()) launch_slab<R, 13, 2>(c, Mr, N, K, A, lda, Wp, nt_total, nt0, dst, ldd);
-                       else launch_slab<R, 13, 1>(c, Mr, N, K, A, lda, Wp, nt_total, nt0, dst, ldd); }
+  // (two m-tiles per warp for the 10- and 13-tile widths -- each W fragment feeding two DMMAs -- need 233 registers, i.e. one
+  // CTA per SM: measured 21.4 against 25.8 TFLOP/s at N = 101, K = 301, so the wide slabs keep one m-tile per warp)
+  else if (nt <= 10) launch_slab<R, 10, 1>(c, Mr, N, K, A, lda, Wp, nt_total, nt0, dst, ldd);
+  else if (nt <= 13) launch_slab<R, 13, 1>(c, Mr, N, K, A, lda, Wp, nt_total, nt0, dst, ldd);
   else launch_slab<R, 16, 1>(c, Mr, N, K, A, lda, Wp, nt_total, nt0, dst, ldd);
 }
 

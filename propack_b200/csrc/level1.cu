@@ -229,10 +229,6 @@ inline int push_ctas() {   // read at every call: cheap, and lets one process co
   const int v = e ? std::atoi(e) : 64;   // measured on 8 GPUs, config 5: 32 -> 1050 ms, 48/64 -> 954-977, 96 -> 990, 128/148 -> 1005 (pre y-prefetch)
   return std::min(148, std::max(1, v));
 }
-inline int push_depth() {
-  const char* e = std::getenv("PROPACK_B200_PUSH_DEPTH");
-  return e ? std::atoi(e) : 4;
-}
 template <class T>
 void k_scal_push(Context& c, long n, long ld, T* x, real_t<T> a, void** bases_dev, int rank, int world, unsigned long long epoch,
                  T* self_slice) {
@@ -245,8 +241,7 @@ void k_scal_push(Context& c, long n, long ld, T* x, real_t<T> a, void** bases_de
   PB_CUDA(cudaEventRecord(c.ev_fork, c.stream));
   PB_CUDA(cudaStreamWaitEvent(c.stream2, c.ev_fork, 0));
   const int grid = (int)std::min<long>(push_ctas(), std::max<long>(1, ((n + Pack<T>::N - 1) / Pack<T>::N + kThreads - 1) / kThreads));
-  if (push_depth() >= 8) push_kernel<T, 8><<<grid, kThreads, 0, c.stream2>>>(n, ld, x, bases_dev, rank, world, c.tickets8, epoch);
-  else push_kernel<T, 4><<<grid, kThreads, 0, c.stream2>>>(n, ld, x, bases_dev, rank, world, c.tickets8, epoch);
+  push_kernel<T, 4><<<grid, kThreads, 0, c.stream2>>>(n, ld, x, bases_dev, rank, world, c.tickets8, epoch);
   PB_LAUNCH_CHECK();
   c.ctr.launches += 1;
 }

@@ -22,8 +22,9 @@ def run_dist_check(world, env, port=29517, timeout=1500):
 @pytest.mark.gpu
 @pytest.mark.parametrize("env", [{}, {"PROPACK_B200_SPMV_PHASES": "1", "DIST_CHECK_LARGE_ROWS": "0"},
                                  {"PROPACK_B200_FUSED_COLLECTIVES": "0", "DIST_CHECK_LARGE_ROWS": "0"},
-                                 {"PROPACK_B200_SPMV": "csr", "DIST_CHECK_LARGE_ROWS": "0"}],
-                         ids=["fused-phased-sell", "fused-one-phase", "nccl-only", "csr-kernel"])
+                                 {"PROPACK_B200_SPMV": "csr", "DIST_CHECK_LARGE_ROWS": "0"},
+                                 {"PROPACK_B200_PUSH": "ce", "DIST_CHECK_LARGE_ROWS": "0"}],
+                         ids=["fused-phased-sell", "fused-one-phase", "nccl-only", "csr-kernel", "copy-engine-transport"])
 def test_row_sharded_drivers_all_gpus(env):
     import torch
     n = torch.cuda.device_count()

@@ -33,11 +33,8 @@ for st in settings:
     kv = dict(x.split("=") for x in st.split(","))
     os.environ["PROPACK_B200_SPMV_PHASES"] = kv.get("PHASES", "4")
     os.environ["PROPACK_B200_PUSH_CTAS"] = kv.get("PUSH", "64")
-    os.environ["PROPACK_B200_PUSH_DEPTH"] = kv.get("DEPTH", "4")      # 128-bit packs in flight per thread of the push kernel
     os.environ["PROPACK_B200_SELL_VARIANT"] = kv.get("VARIANT", "1")  # SELL kernel shape (sell.cu): 1 = 8 chains x 32 warps/SM, 2 = 4 chains x 64 warps/SM, ...
     os.environ["PROPACK_B200_PUSH"] = kv.get("MODE", "sm")            # sm (push kernel, default) | ce (copy engines)
-    os.environ["PROPACK_B200_PUSH_CHAINS"] = kv.get("CHAINS", "2")    # concurrent chains of peer copies in the push graph
-    os.environ["PROPACK_B200_PUSH_GRAPH"] = kv.get("GRAPH", "1")      # 0: plain stream-ordered copies instead of the CUDA graph
     op = pdist.ShardedOperator(A, rank, world)
     sv = pdist.Solver(op, lanmax + 1, lanmax)
 
