@@ -193,7 +193,9 @@ template <class R> void gemm_real(Context& c, long Mr, int N, int K, R* A, long 
 template <class R> std::vector<double> pack_w(int K, int N, const R* W, int ldw, int* nt_total) {
   const int ksteps = (K + 3) / 4, nt = (N + 7) / 8;
   const int ksteps_pad = (ksteps + GK_KS_MAX - 1) / GK_KS_MAX * GK_KS_MAX;   // whole chunks: the kernel copies them unconditionally
-  std::vector<double> out((size_t)ksteps_pad * nt * 32, 0.0);
+  // + 16 zero tiles of slack: a slab launched with NT rounded up (11 -> 13 tiles, ...) copies NT tiles per k-step starting at its
+  // first tile, i.e. up to NT-1 tiles past the end of the last k-step (their products land in columns >= N and are discarded)
+  std::vector<double> out(((size_t)ksteps_pad * nt + 16) * 32, 0.0);
   for (int s = 0; s < ksteps; ++s)
     for (int j = 0; j < nt; ++j)
       for (int t = 0; t < 32; ++t) {
