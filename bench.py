@@ -318,7 +318,7 @@ def run_reference(args):
         "cpu_baseline": {"value": value, "unit": "steps/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    if not args.no_scipy and time.perf_counter() - t_start < SCIPY_START_BEFORE_S:
+    if not args.no_scipy and args.gpus == 1 and time.perf_counter() - t_start < SCIPY_START_BEFORE_S:   # (once per scaling sweep is enough)
         sc = scipy_svdp_sample(args.workload)
         if sc:
             line["scipy_svdp"] = sc

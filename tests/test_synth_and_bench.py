@@ -51,3 +51,35 @@ def test_bench_workload_generators_are_deterministic(name):
     cfg = bench.config_dict(name, A1, k, kmax, tol)
     assert cfg["nnz"] == A1.nnz and cfg["rows"] == A1.shape[0] and "workload" in cfg
     assert bench.wl_dtype(name)[0] == ("c128" if np.iscomplexobj(A1.data) else "f64")
+
+
+def test_reference_arm_prints_one_contract_line():
+    """`bench.py --impl reference` (the CPU oracle's FULL solve of the workload) on the tiny replica: one JSON line with the keys the
+    bench contract names, a converged solve, and SciPy's `_svdp` cross-check agreeing with the oracle on sigma_1."""
+    import json
+    import subprocess
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", "c2-tiny", "--steps", "1",
+                        "--warmup", "0"], capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert p.returncode == 0, p.stderr[-2000:]
+    lines = [ln for ln in p.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for key in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+                "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert key in d, key
+    assert d["impl"] == "reference" and d["info"] == 0 and d["converged"] == 10 and d["value"] > 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+    sc = d.get("scipy_svdp")
+    if sc and "sigma_1" in sc:
+        assert abs(sc["sigma_1"] - d["sigma_1"]) < 1e-10 * d["sigma_1"]
+
+
+def test_at_size_fixture_is_consistent():
+    """tests/golden/c5_small_irl.npz (tools/make_golden_atsize.py): the oracle and SciPy's PROPACK translation agree on all 100 values of
+    the config-5 pattern at 1M rows, and the fixture describes the matrix bench.make_matrix('c5-small') builds."""
+    g = np.load(os.path.join(ROOT, "tests", "golden", "c5_small_irl.npz"))
+    so, ss = g["sigma_oracle"], g["sigma_scipy_svdp"]
+    assert so.size == 100 and np.all(np.diff(so) <= 0) and int(g["k"]) == 100 and int(g["dim"]) == 300 and int(g["p"]) == 200
+    assert np.max(np.abs(so - ss) / so) < 1e-12
+    assert tuple(g["shape"]) == (1_000_000, 1_000_000) and int(g["nsteps"]) == 1100 and int(g["nrestart"]) == 4
