@@ -715,8 +715,8 @@ def run_ours_sharded(args):
             "parallelism": ((f"rows of the dense A and of U, and V-vectors, block-sharded over {world} GPUs; A x = NCCL all-gather of the "
                              f"n-vector + local GEMV, A^T u = local GEMV^T + NCCL all-reduce of the n coefficients; reorthogonalisation "
                              f"coefficients and norm partials all-reduced inside the producing kernels over NVLink peer memory") if dense else
-                            (f"rows of A and U, and V-vectors, block-sharded over {world} GPUs; the SpMV input travels slice by slice over "
-                             f"NVLink by copy engines (a CUDA graph of chained peer copies + arrival-flag copies on a side stream) while the "
+                            (f"rows of A and U, and V-vectors, block-sharded over {world} GPUs; the SpMV input is pushed slice by slice over "
+                             f"NVLink peer memory by a thin side-stream kernel (64 CTAs, ring order, one arrival flag per slice) while the "
                              f"phase-split SpMV consumes the slices that have landed; all-reduce of reorthogonalisation coefficients and "
                              f"norm partials fused into the producing kernels (NCCL for the un-staged products); collectives_total counts "
                              f"the NCCL calls that remain")),
