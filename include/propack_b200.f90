@@ -52,6 +52,45 @@ module propack_b200
       integer(c_long), value :: lda
       real(c_double), intent(in) :: a(lda, *)
     end function
+    ! ---- multi-GPU, one process (one MPI rank) per GPU: include/propack_b200.h "multi-GPU" ----------------------------
+    ! int propack_b200_comm_unique_id(void* id128_out)            rank 0 only; broadcast the 128 bytes (e.g. MPI_Bcast)
+    integer(c_int) function propack_b200_comm_unique_id(id128) bind(C, name='propack_b200_comm_unique_id')
+      import :: c_int, c_char
+      character(kind=c_char), intent(out) :: id128(128)
+    end function
+    ! int propack_b200_comm_init(int rank, int world, const void* id128)        collective
+    integer(c_int) function propack_b200_comm_init(rank, world, id128) bind(C, name='propack_b200_comm_init')
+      import :: c_int, c_char
+      integer(c_int), value :: rank, world
+      character(kind=c_char), intent(in) :: id128(128)
+    end function
+    integer(c_int) function propack_b200_comm_finalize() bind(C, name='propack_b200_comm_finalize')
+      import :: c_int
+    end function
+    ! void propack_b200_shard_bounds(long dim, int world, int rank, long* lo, long* hi)     rank owns [lo, hi), 0-based
+    subroutine propack_b200_shard_bounds(dim, world, rank, lo, hi) bind(C, name='propack_b200_shard_bounds')
+      import :: c_int, c_long
+      integer(c_long), value :: dim
+      integer(c_int), value :: world, rank
+      integer(c_long), intent(out) :: lo, hi
+    end subroutine
+    ! int propack_b200_csr_create_sharded_d(int mg, int ng, row_rowptr, row_colind, row_values, colt_rowptr, colt_rowind,
+    !                                       colt_values, int index_base)      this rank's rows of A and columns of A (transposed)
+    integer(c_int) function propack_b200_csr_create_sharded_d(mg, ng, row_rowptr, row_colind, row_values, colt_rowptr, &
+        colt_rowind, colt_values, index_base) bind(C, name='propack_b200_csr_create_sharded_d')
+      import :: c_int, c_double
+      integer(c_int), value :: mg, ng, index_base
+      integer(c_int), intent(in) :: row_rowptr(*), row_colind(*), colt_rowptr(*), colt_rowind(*)
+      real(c_double), intent(in) :: row_values(*), colt_values(*)
+    end function
+    ! int propack_b200_dense_create_sharded_d(int mg, int ng, const double* A_rows, long lda)      this rank's rows of a dense A
+    integer(c_int) function propack_b200_dense_create_sharded_d(mg, ng, a_rows, lda) &
+        bind(C, name='propack_b200_dense_create_sharded_d')
+      import :: c_int, c_long, c_double
+      integer(c_int), value :: mg, ng
+      integer(c_long), value :: lda
+      real(c_double), intent(in) :: a_rows(lda, *)
+    end function
     ! int propack_b200_op_destroy(int handle)
     integer(c_int) function propack_b200_op_destroy(handle) bind(C, name='propack_b200_op_destroy')
       import :: c_int
