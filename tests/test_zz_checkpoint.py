@@ -1,4 +1,5 @@
-"""Checkpoint / resume of the Lanczos factorisation (propack_b200/checkpoint.py): file round trip on the CPU, resume on the GPU."""
+"""Checkpoint / resume of the Lanczos factorisation (propack_b200/checkpoint.py): file round trip on the CPU, resume on the GPU.
+(Named to be collected last: it builds on entry points the earlier files test.)"""
 import os
 import sys
 
