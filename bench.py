@@ -57,7 +57,7 @@ DENSE_CPU_ROWS = {"c3": 100_000, "c3-small": 20_000}   # rows of the CPU arm's r
 IRL_P = {"c5": 200, "c5-small": 200, "c3": 100, "c3-small": 50}   # workloads solved with DLANSVD_IRL: shifts per restart (kmax column = dim)
 IRL_MAXITER = 50
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel at working size, from the committed
-# `ncu --set full` captures (profiles/r02_ncu_extract.txt); filled in by hand from those files, None = not captured
+# `ncu --set full` captures (profiles/r02_ncu_extract_c5.txt); filled in by hand from those files, None = not captured
 # (SpMV: per product = the 2 column-panel launches of spmv_sell_kernel on config 5, mean of A x and A^T u; reorth: one GEMV
 # pair gemv_t_tma_kernel + gemv_n_kernel at L = 1e7, l = 300 -- 48.27 GB against 48.24 GB algorithmic)
 NCU_TRAFFIC_BYTES_PER_LAUNCH = {("c5", "spmv"): 1.676e9, ("c5", "reorth"): 48.27e9, ("c2", "spmv"): 140.03e6 + 5.3e6, ("c2", "reorth"): None}
