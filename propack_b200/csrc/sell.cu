@@ -24,7 +24,8 @@
 //
 // Column blocking.  A gathered vector larger than the L2 can keep (x = 80 MB on BASELINE config 5) makes most gathers
 // miss to DRAM at 32-byte sector granularity: ncu measured 3.1 GB of DRAM reads per product against 1.4 GB algorithmic
-// (profiles/r02_ncu_extract_c5.txt).  Operands are therefore split by COLUMN RANGE into panels ("phases") whose slice of x
+// with the operand in one piece, 1.68 GB with two panels (profiles/r02_ncu_extract_c5.txt: algorithmic + the second panel's
+// read-modify-write of y).  Operands are therefore split by COLUMN RANGE into panels ("phases") whose slice of x
 // stays L2-resident: y = sum_g A_g x_g, one launch per panel, accumulating into y (coalesced read-modify-write), the
 // last panel applying the epilogue.  Row-sharded runs (one process per GPU) use the same mechanism with the panels
 // = the source ranks of the gathered vector: panel g waits (in-kernel) only for the arrival flags of its sources, so the
