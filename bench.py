@@ -651,6 +651,14 @@ def run_ours_sharded(args):
         harr = (pin(rows.indptr, np.int32), pin(rows.indices, np.int32), pin(rows.data, np.float64),
                 pin(colt.indptr, np.int32), pin(colt.indices, np.int32), pin(colt.data, np.float64))
     sv.close(); op.close()
+    # caller-owned result buffers in pinned memory (allocated once, outside the timed region), as in the 1-GPU e2e leg: the
+    # copy back of this rank's slices of U and V then runs at PCIe speed instead of through pageable memory
+    rb, cb = pdist.shard_bounds(m, world, rank), pdist.shard_bounds(n, world, rank)
+    try:
+        Upin = torch.empty((k, max(rb[1] - rb[0], 1)), dtype=torch.float64).pin_memory().numpy().T
+        Vpin = torch.empty((k, max(cb[1] - cb[0], 1)), dtype=torch.float64).pin_memory().numpy().T
+    except Exception:
+        Upin = Vpin = None
     e2e_t, e2e_steps = [], 0
     for i in range(0 if args.no_e2e else 1 + max(1, min(args.steps, 3))):
         barrier()
@@ -667,9 +675,9 @@ def run_ours_sharded(args):
         sv2.set_start(u0)
         propack_b200.reset_counters()
         if args.workload in IRL_P:
-            r = sv2.lansvd_irl("L", kmax, IRL_P[args.workload], k, IRL_MAXITER, tol=tol, cgs=True)
+            r = sv2.lansvd_irl("L", kmax, IRL_P[args.workload], k, IRL_MAXITER, tol=tol, cgs=True, U_out=Upin, V_out=Vpin)
         else:
-            r = sv2.lansvd(k, kmax, tol=tol, cgs=True)
+            r = sv2.lansvd(k, kmax, tol=tol, cgs=True, U_out=Upin, V_out=Vpin)
         torch.cuda.synchronize()
         barrier()
         dt = time.perf_counter() - t0
@@ -728,8 +736,8 @@ def run_ours_sharded(args):
                     "time_to_k_triplets_s": float(np.mean(e2e_t)) if e2e_t else None,
                     "path": ("per rank: propack_b200_dense_create_synthetic_sharded_d (this rank's rows generated on the device) + solver "
                              "session + local U,V slices and sigma copied back; bytes are per rank") if dense else
-                            ("per rank: propack_b200_csr_create_sharded_d (pinned host shard) + solver session + local U,V slices and "
-                             "sigma copied back; bytes are per rank")},
+                            ("per rank: propack_b200_csr_create_sharded_d (pinned host shard) + solver session + local U,V slices (into pinned "
+                             "result buffers) and sigma copied back; bytes are per rank")},
             "roofline": roofline, "phases_ms_profiled_solve": ph, "profiled_solve_ms": pms, "clocks": clk,
         }
         sys.stdout.flush()

@@ -189,7 +189,8 @@ class Solver:
             loc = np.zeros(1, dtype=self.op.dtype)
         check(lib().propack_b200_solver_set_start(C.c_int(self.id), _p(loc)), "set_start")
 
-    def lansvd(self, k, kmax, tol=0.0, delta=None, eta=None, anorm=0.0, cgs=True, elr=True, jobu=True, jobv=True):
+    def lansvd(self, k, kmax, tol=0.0, delta=None, eta=None, anorm=0.0, cgs=True, elr=True, jobu=True, jobv=True, U_out=None,
+               V_out=None):
         pfx = self.op.pfx
         R = REAL[pfx]
         sigma = np.zeros(max(k, 1), dtype=R); bnd = np.zeros(max(k, 1), dtype=R)
@@ -198,10 +199,10 @@ class Solver:
         kk, info = C.c_int(k), C.c_int(0)
         check(lib().propack_b200_solver_lansvd(C.c_int(self.id), C.c_int(int(jobu)), C.c_int(int(jobv)), C.byref(kk), C.c_int(kmax),
                                                _p(sigma), _p(bnd), C.c_double(tol), _p(dopt), _p(iopt), C.byref(info)), "solver_lansvd")
-        return self._result(kk.value, info.value, sigma, bnd, jobu, jobv)
+        return self._result(kk.value, info.value, sigma, bnd, jobu, jobv, U_out, V_out)
 
     def lansvd_irl(self, which, dim, p, neig, maxiter, tol=0.0, delta=None, eta=None, anorm=0.0, min_relgap=0.002, cgs=True,
-                   elr=True, jobu=True, jobv=True):
+                   elr=True, jobu=True, jobv=True, U_out=None, V_out=None):
         pfx = self.op.pfx
         R = REAL[pfx]
         sigma = np.zeros(max(neig, 1), dtype=R); bnd = np.zeros(max(neig, 1), dtype=R)
@@ -212,19 +213,32 @@ class Solver:
         check(lib().propack_b200_solver_lansvd_irl(C.c_int(self.id), C.c_int(smallest), C.c_int(int(jobu)), C.c_int(int(jobv)),
                                                    C.byref(d), C.c_int(p), C.byref(ne), C.c_int(maxiter), _p(sigma), _p(bnd),
                                                    C.c_double(tol), _p(dopt), _p(iopt), C.byref(info)), "solver_lansvd_irl")
-        return self._result(ne.value, info.value, sigma, bnd, jobu, jobv)
+        return self._result(ne.value, info.value, sigma, bnd, jobu, jobv, U_out, V_out)
 
-    def _result(self, k, info, sigma, bnd, jobu, jobv):
+    def _result(self, k, info, sigma, bnd, jobu, jobv, U_out=None, V_out=None):
+        """This rank's row slices of the k Ritz vectors.  `U_out` / `V_out`: caller-owned result buffers (e.g. pinned host memory,
+        which the device-to-host copy reaches at PCIe speed) -- Fortran-ordered, the operator's dtype, at least
+        max(m_local, 1) / max(n_local, 1) rows and k columns; otherwise fresh (pageable) arrays are returned."""
         out = {"k": k, "info": info, "sigma": sigma[:k].copy(), "bnd": bnd[:k].copy(), "U": None, "V": None}
         dt = self.op.dtype
+
+        def buffer(given, rows, name):
+            rows = max(rows, 1)
+            if given is None:
+                return np.zeros((rows, k), dtype=dt, order="F")
+            if (given.dtype != dt or given.ndim != 2 or not given.flags.f_contiguous or given.shape[0] < rows or given.shape[1] < k
+                    or not given.flags.writeable):
+                raise ValueError(f"{name} must be a writeable Fortran-ordered {dt} array with >= {rows} rows and >= {k} columns")
+            return given
+
         if jobu and k > 0:
-            U = np.zeros((max(self.m_local, 1), k), dtype=dt, order="F")
+            U = buffer(U_out, self.m_local, "U_out")
             check(lib().propack_b200_solver_get_u(C.c_int(self.id), C.c_int(k), _p(U), C.c_long(U.shape[0])), "get_u")
-            out["U"] = U[:self.m_local]
+            out["U"] = U[:self.m_local, :k]
         if jobv and k > 0:
-            V = np.zeros((max(self.n_local, 1), k), dtype=dt, order="F")
+            V = buffer(V_out, self.n_local, "V_out")
             check(lib().propack_b200_solver_get_v(C.c_int(self.id), C.c_int(k), _p(V), C.c_long(V.shape[0])), "get_v")
-            out["V"] = V[:self.n_local]
+            out["V"] = V[:self.n_local, :k]
         return out
 
     def close(self):

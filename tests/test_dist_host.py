@@ -130,3 +130,45 @@ def test_gloo_world2_sharded_products_match_global():
     for p in procs:
         p.join(timeout=60)
     assert sorted(res) == [(0, True), (1, True)]
+
+
+def test_solver_result_buffers(monkeypatch):
+    """dist.Solver._result: fresh arrays by default; caller-owned (e.g. pinned) Fortran-ordered buffers are filled in place, with their
+    own leading dimension, and unsuitable ones are refused (no device needed: the two copy-back entry points are faked)."""
+    calls = []
+
+    class FakeLib:
+        def _fill(self, which, sid, ncols, ptr, ld):
+            a = np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_double)), shape=(ld.value * ncols.value,))
+            rows = 5 if which == "u" else 3
+            for j in range(ncols.value):
+                a[j * ld.value: j * ld.value + rows] = (100 if which == "u" else 200) + 10 * j + np.arange(rows)
+            calls.append((which, ncols.value, ld.value))
+            return 0
+
+        def propack_b200_solver_get_u(self, sid, ncols, ptr, ld):
+            return self._fill("u", sid, ncols, ptr, ld)
+
+        def propack_b200_solver_get_v(self, sid, ncols, ptr, ld):
+            return self._fill("v", sid, ncols, ptr, ld)
+
+    monkeypatch.setattr(pdist, "lib", lambda: FakeLib())
+    sv = pdist.Solver.__new__(pdist.Solver)
+    sv.id, sv.m_local, sv.n_local = 0, 5, 3           # id 0: close() / __del__ do nothing
+    sv.op = type("Op", (), {"dtype": np.dtype(np.float64)})()
+    sigma = np.array([3.0, 2.0, 1.0]); bnd = np.zeros(3)
+    r = sv._result(2, 0, sigma, bnd, True, True)
+    assert r["U"].shape == (5, 2) and r["V"].shape == (3, 2) and r["U"][4, 1] == 114.0 and r["V"][2, 1] == 212.0
+    assert calls == [("u", 2, 5), ("v", 2, 3)]
+    # caller-owned buffers: more rows and columns than needed, Fortran order (a transposed C array, like a pinned torch tensor)
+    Ub = np.zeros((4, 8)).T; Vb = np.zeros((2, 6)).T
+    assert Ub.flags.f_contiguous and Ub.shape == (8, 4)
+    calls.clear()
+    r = sv._result(2, 0, sigma, bnd, True, True, U_out=Ub, V_out=Vb)
+    assert calls == [("u", 2, 8), ("v", 2, 6)]
+    assert r["U"].shape == (5, 2) and np.shares_memory(r["U"], Ub) and r["U"][0, 0] == 100.0 and r["U"][4, 1] == 114.0
+    assert r["V"].shape == (3, 2) and np.shares_memory(r["V"], Vb) and r["V"][2, 1] == 212.0
+    assert np.array_equal(r["sigma"], [3.0, 2.0])
+    for bad in (np.zeros((8, 4)), np.zeros((4, 8), dtype=np.float32).T, np.zeros((1, 8)).T, np.zeros((4, 4)).T):
+        with pytest.raises(ValueError):
+            sv._result(2, 0, sigma, bnd, True, False, U_out=bad)
