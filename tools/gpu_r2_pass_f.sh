@@ -1,5 +1,7 @@
 #!/bin/bash
 # round 2, pass F (N GPUs): SELL kernel shape x phases on the row-sharded config 5 (short panel rows are latency-bound)
+# (record of what produced profiles/r02_sweep8_c5_*.jsonl: the CHAINS / GRAPH / DEPTH / FUSED keys belong to experiments that were
+#  measured and then removed from the library -- tools/sharded_sweep.py ignores keys it no longer knows)
 mkdir -p gpurun_out
 O=gpurun_out
 N=$(nvidia-smi -L | wc -l)
