@@ -1,8 +1,8 @@
 #!/bin/bash
 # round 2, pass D (N GPUs): parity of the copy-engine all-gather transport (tests/dist_check.py), then one torchrun launch that
+# solves config 5 row-sharded under several transport / phase settings (tools/sharded_sweep.py), then the sharded bench.
 # (record of what produced profiles/r02_sweep8_c5_*.jsonl: the CHAINS / GRAPH / DEPTH / FUSED keys belong to experiments that were
 #  measured and then removed from the library -- tools/sharded_sweep.py ignores keys it no longer knows)
-# solves config 5 row-sharded under several transport / phase settings (tools/sharded_sweep.py), then the sharded bench.
 mkdir -p gpurun_out
 O=gpurun_out
 N=$(nvidia-smi -L | wc -l)

@@ -1,8 +1,8 @@
 #!/bin/bash
 # round 2, pass G (N GPUs): parity of the single-launch phase-split SpMV (tests/dist_check.py), then fused vs per-phase launches x
+# transport on config 5
 # (record of what produced profiles/r02_sweep8_c5_*.jsonl: the CHAINS / GRAPH / DEPTH / FUSED keys belong to experiments that were
 #  measured and then removed from the library -- tools/sharded_sweep.py ignores keys it no longer knows)
-# transport on config 5
 mkdir -p gpurun_out
 O=gpurun_out
 N=$(nvidia-smi -L | wc -l)
