@@ -18,7 +18,8 @@ upload + start vector up, U/V/sigma back) inside the timed region; roofline desc
 of the solve, measured live with CUDA events in a profiled solve of the same workload; cpu_baseline is the CPU oracle (a
 port of the reference, OpenMP) on a bounded sample.  `--impl reference` times the oracle's FULL solve of the same
 workload (same driver, k, tol, start vector: time to k triplets, like for like) on all host cores, plus SciPy's PROPACK
-translation (`scipy.sparse.linalg._svdp`) on a bounded 1/10-scale replica as an independent cross-check.
+translation (`scipy.sparse.linalg._svdp`) on a bounded 1/10-scale replica as an independent cross-check (at --gpus 1 only: once
+per scaling sweep is enough).
 """
 from __future__ import annotations
 
