@@ -9,6 +9,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <exception>
 #include <thread>
 #include <vector>
 
@@ -260,8 +261,13 @@ inline void restart_sweeps(int dim, int k, const R* shift, R* a, R* b, R* P, R* 
     apply_rotations_blocked<R>(dim, dim, Q, dim, rr, t, nthreads);
   };
   std::vector<std::thread> pool;
-  for (int t = 1; t < nthreads; ++t) pool.emplace_back(work, t);
+  int spawned = 1;
+  try {
+    for (; spawned < nthreads; ++spawned) pool.emplace_back(work, spawned);
+  } catch (const std::exception&) {   // no more threads to be had: the caller takes the remaining shares itself
+  }
   work(0);
+  for (int t = spawned; t < nthreads; ++t) work(t);
   for (auto& th : pool) th.join();
 }
 
